@@ -1,0 +1,193 @@
+/*
+ * ssdnerf_b200.h -- C ABI of libssdnerf_b200.so: B200 (sm_100a) kernels for SSDNeRF's two hot paths.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch / ATen types; every pointer is a DEVICE pointer owned by the
+ *     caller unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); kernels are enqueued
+ *     asynchronously on it and nothing synchronises;
+ *   - no hidden allocations: scratch is caller-provided (see the *_workspace_bytes queries);
+ *   - return 0 on success, a negative SSDNERF_ERR_* code otherwise; ssdnerf_last_error() returns a
+ *     thread-local description of the last failure.
+ *
+ * "replaces:" lines cite the reference interface (Lakonik/SSDNeRF @ b9d195d) each function stands in for.
+ */
+#ifndef SSDNERF_B200_H_
+#define SSDNERF_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDNERF_OK 0
+#define SSDNERF_ERR_CUDA (-1)   /* a CUDA runtime / driver call failed */
+#define SSDNERF_ERR_ARG (-2)    /* invalid argument (shape, alignment, unsupported variant) */
+#define SSDNERF_ERR_ARCH (-3)   /* device is not sm_100 */
+
+const char* ssdnerf_last_error(void);
+/* library version and the SM architecture it was compiled for (100) */
+int ssdnerf_version(void);
+int ssdnerf_compiled_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Legacy per-op entry points == the reference's pybind FFI, one to one.
+ *    replaces: lib/ops/raymarching/src/raymarching.h:7-18 + bindings.cpp:5-18 (module `_raymarching`)
+ *              lib/ops/shencoder/src/shencoder.h:9,12 + bindings.cpp:5-6    (module `_shencoder`)
+ *    Same argument order and meaning; at::Tensor -> pointer; fp32 only; caller allocates (and, where
+ *    the reference's Python wrapper does, zero-fills) every output.
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces: near_far_from_aabb (raymarching.cu:148-156, kernel :92-145) */
+int ssdnerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                               float* nears, float* fars, void* stream);
+/* replaces: sph_from_ray (raymarching.cu:200-208) -- unused by the model, kept for API completeness */
+int ssdnerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream);
+/* replaces: morton3D / morton3D_invert (raymarching.cu:229-232, :257-260) */
+int ssdnerf_morton3D(const int* coords, uint32_t N, int* indices, void* stream);
+int ssdnerf_morton3D_invert(const int* indices, uint32_t N, int* coords, void* stream);
+/* replaces: packbits (raymarching.cu:292-300); N = number of OUTPUT bytes; grid is fp32 or fp16 (grid_is_half) */
+int ssdnerf_packbits(const void* grid, int grid_is_half, uint32_t N, float thresh, uint8_t* bitfield, void* stream);
+/* replaces: march_rays_train (raymarching.cu:484-492, kernel :312-482); counter = int[2] {points, rays} */
+int ssdnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                             uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                             const float* fars, float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
+                             const float* noises, void* stream);
+/* replaces: composite_rays_train_forward / _backward (raymarching.cu:584-592, :690-698) */
+int ssdnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int* rays,
+                                         uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
+                                         float* image, void* stream);
+int ssdnerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                          const float* rgbs, const float* deltas, const int* rays, const float* weights_sum,
+                                          const float* image, uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                          float* grad_rgbs, void* stream);
+/* replaces: march_rays (raymarching.cu:815-822, kernel :706-812); noises may be NULL (== zeros) */
+int ssdnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
+                       const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                       const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                       const float* noises, void* stream);
+/* replaces: composite_rays (raymarching.cu:916-922, kernel :826-913) */
+int ssdnerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive, float* rays_t,
+                           const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                           float* image, void* stream);
+/* replaces: sh_encode_forward / sh_encode_backward (shencoder.cu:386-399, :416-440); degree C <= 4 */
+int ssdnerf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t C, int calc_grad_inputs,
+                              float* dy_dx, void* stream);
+int ssdnerf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t C, const float* dy_dx,
+                               float* grad_inputs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Fused triplane renderer (inference).
+ *    replaces, as ONE launch sequence with no host synchronisation:
+ *      lib/models/decoders/base_volume_renderer.py:79-123  (eval branch of VolumeRenderer.forward:
+ *          K1 near/far + host loop of march_rays -> point_decode -> composite_rays -> compaction)
+ *      lib/models/decoders/triplane_decoder.py:119-179     (TriPlaneDecoder.point_decode)
+ *      lib/core/utils/nerf_utils.py:17-61                  (get_cam_rays, when rays are generated in-kernel)
+ *      lib/models/autodecoders/base_nerf.py:520-523        (image + bg * (1 - weights_sum), optional)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Decoder variants (template instantiations). */
+#define SSDNERF_DEC_P 0 /* shipped configs: base 3*6->64, density 64->1, dir_net 16->64, color 64->3
+                           (configs/paper_cfgs/ssdnerf_cars_uncond.py:40-51) */
+#define SSDNERF_DEC_S 1 /* TriPlaneDecoder class defaults: base 3*32->128, density 128->1, color (128+16)->128->3
+                           (lib/models/decoders/triplane_decoder.py:24-39) */
+
+/* Size in floats of the packed fp32 decoder-weight blob for a variant (layout: ssdnerf_b200/decoder_pack.py). */
+size_t ssdnerf_decoder_blob_floats(int variant);
+
+/* Re-layout one batch of triplanes for the gather:
+ *   code  fp32 [B][3][C][Hp][Wp]  (reference layout, triplane_decoder.py:123)
+ *   -> planes [B][3][Hp][Wp][Cpad] channels-last, fp32 (variant P, Cpad = 8) or fp16 (variant S, Cpad = 32). */
+size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp);
+int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, uint32_t Hp, uint32_t Wp, void* planes,
+                        void* stream);
+
+typedef struct ssdnerf_render_args {
+    int variant;              /* SSDNERF_DEC_* */
+    uint32_t num_scenes;      /* B */
+    uint32_t rays_per_scene;  /* N (explicit rays) or V*h*w (camera mode) */
+    /* --- rays: either explicit ... */
+    const float* rays_o;      /* [B][N][3] or NULL */
+    const float* rays_d;      /* [B][N][3] or NULL */
+    /* --- ... or generated in-kernel from cameras (nerf_utils.py:17-61) */
+    const float* poses;       /* [B][V][4][4] row-major c2w, or NULL */
+    const float* intrinsics;  /* [B][V][4] = fx, fy, cx, cy, or NULL */
+    uint32_t num_views, img_h, img_w;
+    /* --- scene */
+    const void* planes;       /* from ssdnerf_pack_planes */
+    uint32_t plane_h, plane_w;
+    const uint8_t* bitfield;  /* [B][H^3/8], morton order, LSB first */
+    uint32_t grid_size;       /* H */
+    const float* decoder_blob;/* packed weights, shared by all scenes */
+    const float* dt_gamma;    /* [B] or NULL (== 0) */
+    float bound, min_near, T_thresh, bg_color;
+    uint32_t max_steps;
+    int emulate_schedule;     /* 1: reproduce the reference host loop's per-scene sample budget exactly
+                                    (n_step = clamp(N / n_alive, 1, 8) quanta until step >= max_steps) */
+    /* --- outputs, [B][N] / [B][N][3]; any may be NULL except image + weights_sum */
+    float* weights_sum;
+    float* depth;
+    float* image;             /* un-blended, == TriPlaneDecoder.forward()['image'] */
+    float* rgb_blend;         /* image + bg_color * (1 - weights_sum), optional */
+    int32_t* num_samples;     /* samples composited per ray, optional */
+    int32_t* voxel_trace;     /* optional [B][N][trace_cap] occupancy-bit index of every composited sample (-1 padded) */
+    uint32_t trace_cap;
+    /* --- scratch */
+    void* workspace;          /* >= ssdnerf_render_workspace_bytes(...) bytes, 16-byte aligned */
+    size_t workspace_bytes;
+} ssdnerf_render_args;
+
+size_t ssdnerf_render_workspace_bytes(uint32_t num_scenes, uint32_t rays_per_scene, uint32_t max_steps);
+int ssdnerf_render_fwd(const ssdnerf_render_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. Occupancy-grid builder.
+ *    replaces: lib/models/autodecoders/base_nerf.py:318-389 (update_extra_state, full-update branch:
+ *              jittered voxel centres -> morton3D -> point_density_decode -> EMA max -> mean -> packbits)
+ *    Two launches per iteration: ssdnerf_density_update (decode + max + per-block partial sums) then
+ *    ssdnerf_density_pack (threshold = min(mean, density_thresh), bit pack).  No host sync.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ssdnerf_density_workspace_bytes(uint32_t num_scenes, uint32_t grid_size);
+int ssdnerf_density_update(int variant, const void* planes, uint32_t plane_h, uint32_t plane_w, const float* decoder_blob,
+                           uint32_t num_scenes, uint32_t grid_size, float bound,
+                           const float* jitter,   /* [G^3][3] uniform [0,1) in ij-meshgrid order (== torch.rand_like of
+                                                     base_nerf.py:344), shared by all scenes; NULL = voxel centres */
+                           float decay, void* density_grid, int grid_is_half, void* workspace, void* stream);
+int ssdnerf_density_pack(const void* density_grid, int grid_is_half, uint32_t num_scenes, uint32_t grid_size,
+                         float density_thresh, uint8_t* bitfield, float* thresh_out /* [1], optional */,
+                         void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. UNet building blocks of the DDIM loop (tcgen05 tensor-core GEMM / implicit-GEMM convolution +
+ *    memory-bound glue kernels).  Activations are NHWC fp16; accumulation is fp32.
+ *    replaces: cuDNN/cuBLAS calls under lib/models/architecture/ddpm/denoising.py:191-216 and
+ *              modules.py:28-48 (+ mmgen 0.7.2 DenoisingResBlock / NormWithEmbedding / QKVAttention /
+ *              DenoisingDownsample / DenoisingUpsample forwards), and the DDIM algebra of
+ *              lib/models/diffusions/gaussian_diffusion.py:180-240,264-293.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ssdnerf_gemm_args {
+    /* D[m, n] = alpha * sum_{tap,k} A_tap[m, k] * B[tap][n, k] + bias_n[n] + residual[m, n]
+     * A: fp16, viewed as {K, d1, d2, d3} with K contiguous and byte strides a*_strides[0..2] for d1, d2, d3;
+     *    an output tile is 128 rows = a (b1 x b2 x b3) box of (d1, d2, d3); taps = 9 shifts the box origin by
+     *    (kx-1, ky-1) in (d1, d2) with zero fill outside (3x3 convolution, padding 1, stride 1).
+     *    Optional second source a2 is concatenated after a1 along K (channel concat of the UNet skip). */
+    const void* a1; uint64_t a1_strides[3]; uint32_t k1;
+    const void* a2; uint64_t a2_strides[3]; uint32_t k2;
+    uint32_t d1, d2, d3, b1, b2, b3;
+    uint32_t taps;
+    /* B: fp16 {K = k1 + k2, n_rows_b, bx2, bx3}, K contiguous, byte strides b_strides[0..2];
+     *    conv / plain: coordinate 2 = tap; b_batched: coordinates (2, 3) = the tile's (d2, d3) tile indices */
+    const void* b; uint64_t b_strides[3]; uint32_t n, n_rows_b, bx2, bx3; uint32_t b_batched;
+    uint32_t bn;              /* N tile: 0 = auto, else 64 / 128 / 256 */
+    float alpha;
+    const float* bias_n;      /* [n] fp32 or NULL */
+    const void* residual;     /* fp16, addressed like out, or NULL */
+    void* out; uint32_t out_f32; long long so1, so2, so3; /* element strides of d1, d2, d3; columns contiguous */
+} ssdnerf_gemm_args;
+int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDNERF_B200_H_ */

@@ -1,0 +1,34 @@
+"""ad-hoc timing of the fused renderer (not the bench contract; see bench.py)"""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import render_port as rp
+from ssdnerf_b200 import renderer as R
+from tests.common import spiral_poses
+
+dev = torch.device('cuda:0')
+variant = sys.argv[1] if len(sys.argv) > 1 else 'P'
+B, V, res = int(os.environ.get('B', 16)), int(os.environ.get('V', 8)), 128
+vid = R.DEC_P if variant == 'P' else R.DEC_S
+C = 6 if variant == 'P' else 32
+g = torch.Generator().manual_seed(0)
+code = torch.randn(B, 3, C, 128, 128, generator=g).clamp(-2, 2).to(dev)
+params = rp.make_decoder_params(variant, 0)
+blob = R.pack_decoder_blob(params, vid, device=dev)
+planes = R.pack_planes(code, vid)
+bf = torch.from_numpy(rp.sphere_bitfield())[None].repeat(B, 1).to(dev)
+poses = torch.from_numpy(spiral_poses(V))[None].repeat(B, 1, 1, 1).to(dev)
+intr = torch.tensor([131.25, 131.25, 64, 64]).expand(B, V, 4).contiguous().to(dev)
+for emu in (1, 0):
+    for _ in range(3):
+        out = R.render_fwd(vid, planes, (128, 128), bf, blob, poses=poses, intrinsics=intr, img_hw=(res, res), emulate_schedule=bool(emu))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        out = R.render_fwd(vid, planes, (128, 128), bf, blob, poses=poses, intrinsics=intr, img_hw=(res, res), emulate_schedule=bool(emu))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    ns = out['num_samples'].sum().item()
+    rays = B * V * res * res
+    print(f'variant {variant} emulate={emu}: {ms:.3f} ms  rays/s={rays/ms*1e3:.3e}  samples={ns} samples/s={ns/ms*1e3:.3e} mean rgb={out["rgb"].mean().item():.4f}')

@@ -1,0 +1,309 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for the UNet of the DDIM loop.
+//
+//   D[m, n] = alpha * sum_{tap, k} A_tap[m, k] * B[tap][n, k]  (+ bias[n]) (+ residual[m, n])
+//
+// * A is read by TMA straight from the NHWC fp16 activation tensor through a 4-D tensor map
+//   {K, d1, d2, d3}: a 3x3 convolution is 9 K-slabs whose box origin is shifted by (kx-1, ky-1) with the
+//   hardware's out-of-bounds zero fill supplying the padding (no im2col buffer).  A plain / batched GEMM is
+//   the same kernel with taps = 1.  A may be split along K over two tensors (UNet skip concat).
+// * B (weights [taps][N][K] or a batched operand) is K-major too; both land in 128B-swizzled smem tiles.
+// * tcgen05.mma (M=128, N=BN, K=16, fp16 x fp16 -> fp32) accumulates in TMEM; accumulators are double
+//   buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue (TMEM -> regs -> global).
+//
+// Replaces on the reference path: cuDNN Conv2d 3x3/1x1, Conv1d qkv/proj and the attention einsums of
+// lib/models/architecture/ddpm/{denoising,modules}.py (+ mmgen 0.7.2 blocks), see ssdnerf_b200/unet.py.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/ssdnerf_b200.h"
+#include <cuda_fp16.h>
+#include <cstdio>
+
+namespace ssdnerf {
+using namespace tc;
+
+constexpr int kGemmThreads = 192;
+constexpr int kBM = 128, kBK = 64;
+constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+
+struct GemmParams {
+    uint32_t b1, b2, b3;        // box extents along d1, d2, d3 (b1*b2*b3 == 128)
+    uint32_t d1, d2, d3;        // problem extents
+    uint32_t T1, T2, T3;        // tiles along d1, d2, d3
+    uint32_t tiles_n;
+    uint32_t taps;              // 1 or 9
+    uint32_t kc1, kc2;          // 64-wide K chunks taken from A1 / A2 per tap
+    uint32_t n_valid;           // output columns
+    uint32_t b_batched;         // B coords (c2, c3) = (t2, t3) instead of (tap, 0)
+    float alpha;
+    const float* bias_n;
+    const __half* residual;
+    void* out;
+    uint32_t out_f32;
+    long long so1, so2, so3;    // output element strides of d1, d2, d3 (column stride 1)
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+          const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::kStages * kABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty = full + Cfg::kStages;
+    uint64_t* tfull = empty + Cfg::kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
+    const uint32_t total_tiles = tiles_m * p.tiles_n;
+    const uint32_t iters = p.taps * (p.kc1 + p.kc2);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA1); prefetch_tmap(&mapA2); prefetch_tmap(&mapB);
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const uint32_t m_tile = tile % tiles_m, n_tile = tile / tiles_m;
+                const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);
+                for (uint32_t tap = 0; tap < p.taps; ++tap) {
+                    const int ox = (p.taps == 9) ? (int)(tap % 3) - 1 : 0;
+                    const int oy = (p.taps == 9) ? (int)(tap / 3) - 1 : 0;
+                    for (uint32_t j = 0; j < p.kc1 + p.kc2; ++j) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                        const bool first = j < p.kc1;
+                        tma_load_4d(sA + stage * kABytes, first ? &mapA1 : &mapA2, &full[stage],
+                                    (int)((first ? j : j - p.kc1) * kBK), (int)(t1 * p.b1) + ox, (int)(t2 * p.b2) + oy,
+                                    (int)(t3 * p.b3));
+                        tma_load_4d(sB + stage * Cfg::kBBytes, &mapB, &full[stage], (int)(j * kBK), (int)(n_tile * BN),
+                                    p.b_batched ? (int)t2 : (int)tap, p.b_batched ? (int)t3 : 0);
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t it = 0; it < iters; ++it) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_desc_sw128(smem_u32(sA + stage * kABytes));
+                    const uint64_t b_desc = make_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (uint32_t k = 0; k < kBK / 16; ++k)   // advance 16 halves = 32 B = 2 descriptor units along K
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {   // ---------------- epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+        const uint32_t q = (uint32_t)warp & 3u;
+        const uint32_t row = q * 32 + (uint32_t)lane;
+        const uint32_t i1 = row % p.b1, i2 = (row / p.b1) % p.b2, i3 = row / (p.b1 * p.b2);
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const uint32_t m_tile = tile % tiles_m, n_tile = tile / tiles_m;
+            const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);
+            const uint32_t g1 = t1 * p.b1 + i1, g2 = t2 * p.b2 + i2, g3 = t3 * p.b3 + i3;
+            const bool row_ok = g1 < p.d1 && g2 < p.d2 && g3 < p.d3;
+            const long long off = (long long)g1 * p.so1 + (long long)g2 * p.so2 + (long long)g3 * p.so3 + (long long)n_tile * BN;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((q * 32u) << 16) + acc * BN + c0, v);
+                tmem_ld_wait();
+                const uint32_t ncol0 = n_tile * BN + c0;
+                if (row_ok && ncol0 < p.n_valid) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+                    if (p.bias_n) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) f[i] += __ldg(p.bias_n + ncol0 + i);
+                    }
+                    const bool full32 = (ncol0 + 32 <= p.n_valid);
+                    if (p.residual) {
+                        const __half* rp = p.residual + off + c0;
+                        if (full32) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h2[i]); f[8 * g + 2 * i] += t.x; f[8 * g + 2 * i + 1] += t.y; }
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) f[i] += __half2float(rp[i]);
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* op = reinterpret_cast<float*>(p.out) + off + c0;
+                        if (full32) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) reinterpret_cast<float4*>(op)[g] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                        } else {
+                            for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) op[i] = f[i];
+                        }
+                    } else {
+                        __half* op = reinterpret_cast<__half*>(p.out) + off + c0;
+                        if (full32) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 o;
+                                __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[8 * g + 2 * i], f[8 * g + 2 * i + 1]);
+                                reinterpret_cast<uint4*>(op)[g] = o;
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) op[i] = __float2half_rn(f[i]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+// ---------------------------------------------------------------- host side: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// fp16 4-D map: dims {K, e1, e2, e3}, byte strides {s1, s2, s3} (K contiguous), box {64, x1, x2, x3}, SWIZZLE_128B
+static int make_map_4d(CUtensorMap* m, const void* base, uint64_t K, uint64_t e1, uint64_t e2, uint64_t e3, uint64_t s1, uint64_t s2,
+                       uint64_t s3, uint32_t x1, uint32_t x2, uint32_t x3) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return set_error_msg(SSDNERF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    if (((uintptr_t)base & 15u) || (s1 & 15u) || (s2 & 15u) || (s3 & 15u))
+        return set_error_msg(SSDNERF_ERR_ARG, "gemm: TMA operands need 16-byte aligned base and strides");
+    cuuint64_t dims[4] = {K, e1, e2, e3};
+    cuuint64_t strides[3] = {s1, s2, s3};
+    cuuint32_t box[4] = {64, x1, x2, x3};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): dims {%llu,%llu,%llu,%llu} box {64,%u,%u,%u}", (int)r,
+                 (unsigned long long)K, (unsigned long long)e1, (unsigned long long)e2, (unsigned long long)e3, x1, x2, x3);
+        return set_error_msg(SSDNERF_ERR_CUDA, buf);
+    }
+    return 0;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const GemmParams& p, int sms,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        attr = true;
+    }
+    const uint32_t total = p.T1 * p.T2 * p.T3 * p.tiles_n;
+    const uint32_t grid = total < (uint32_t)sms ? total : (uint32_t)sms;
+    k_gemm_tc<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(mA1, mA2, mB, p);
+    SSDNERF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ssdnerf
+
+using namespace ssdnerf;
+
+extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || !a->a1 || !a->b || !a->out) return set_error_msg(SSDNERF_ERR_ARG, "gemm: a1, b and out are required");
+    if (a->k1 == 0 || a->k1 % 64 || a->k2 % 64) return set_error_msg(SSDNERF_ERR_ARG, "gemm: K extents must be multiples of 64");
+    if (a->b1 * a->b2 * a->b3 != 128) return set_error_msg(SSDNERF_ERR_ARG, "gemm: b1*b2*b3 must be 128");
+    if (a->taps != 1 && a->taps != 9) return set_error_msg(SSDNERF_ERR_ARG, "gemm: taps must be 1 or 9");
+    if (a->taps == 9 && a->b_batched) return set_error_msg(SSDNERF_ERR_ARG, "gemm: conv taps and batched B are exclusive");
+    if (a->n == 0 || a->d1 == 0 || a->d2 == 0 || a->d3 == 0) return 0;
+    const int bn = a->bn ? a->bn : (a->n > 128 ? 256 : (a->n > 64 ? 128 : 64));
+    if (bn != 64 && bn != 128 && bn != 256) return set_error_msg(SSDNERF_ERR_ARG, "gemm: bn must be 64, 128 or 256");
+    if (a->residual && a->out_f32 == 0 && a->residual == a->out) { /* in-place residual add is fine: same thread reads then writes */ }
+
+    GemmParams p{};
+    p.b1 = a->b1; p.b2 = a->b2; p.b3 = a->b3; p.d1 = a->d1; p.d2 = a->d2; p.d3 = a->d3;
+    p.T1 = div_up(a->d1, a->b1); p.T2 = div_up(a->d2, a->b2); p.T3 = div_up(a->d3, a->b3);
+    p.tiles_n = div_up(a->n, (uint32_t)bn);
+    p.taps = a->taps; p.kc1 = a->k1 / 64; p.kc2 = a->a2 ? a->k2 / 64 : 0; p.n_valid = a->n; p.b_batched = a->b_batched;
+    p.alpha = a->alpha; p.bias_n = a->bias_n; p.residual = (const __half*)a->residual; p.out = a->out; p.out_f32 = a->out_f32;
+    p.so1 = a->so1; p.so2 = a->so2; p.so3 = a->so3;
+    const uint64_t ktot = (uint64_t)a->k1 + (a->a2 ? a->k2 : 0);
+
+    CUtensorMap mA1, mA2, mB;
+    if (int e = make_map_4d(&mA1, a->a1, a->k1, a->d1, a->d2, a->d3, a->a1_strides[0], a->a1_strides[1], a->a1_strides[2], a->b1, a->b2, a->b3)) return e;
+    if (a->a2) {
+        if (int e = make_map_4d(&mA2, a->a2, a->k2, a->d1, a->d2, a->d3, a->a2_strides[0], a->a2_strides[1], a->a2_strides[2], a->b1, a->b2, a->b3)) return e;
+    } else {
+        mA2 = mA1;
+    }
+    // B: {K, N, x2, x3}; box {64, bn, 1, 1}
+    if (int e = make_map_4d(&mB, a->b, ktot, a->n_rows_b ? a->n_rows_b : a->n, a->bx2 ? a->bx2 : 1, a->bx3 ? a->bx3 : 1, a->b_strides[0],
+                            a->b_strides[1], a->b_strides[2], (uint32_t)bn, 1, 1)) return e;
+
+    int dev = 0, sms = 0;
+    SSDNERF_CUDA_OK(cudaGetDevice(&dev));
+    SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (bn == 256) return launch_gemm<256>(mA1, mA2, mB, p, sms, stream);
+    if (bn == 128) return launch_gemm<128>(mA1, mA2, mB, p, sms, stream);
+    return launch_gemm<64>(mA1, mA2, mB, p, sms, stream);
+}

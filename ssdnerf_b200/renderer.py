@@ -1,0 +1,128 @@
+"""Python front-end of the fused triplane renderer (C ABI section 2 of include/ssdnerf_b200.h).
+
+`render_fwd` replaces the eval branch of the reference's ``VolumeRenderer.forward``
+(lib/models/decoders/base_volume_renderer.py:79-123) + ``TriPlaneDecoder.point_decode``
+(lib/models/decoders/triplane_decoder.py:119-179) with one launch sequence and no host sync.
+"""
+import torch
+
+from . import _lib as N
+
+DEC_P = 0   # shipped configs: base 18->64, density 64->1, dir_net 16->64, color 64->3
+DEC_S = 1   # TriPlaneDecoder class defaults: base 96->128, density 128->1, color 144->128->3
+_VARIANT_C = {DEC_P: 6, DEC_S: 32}
+
+
+def detect_variant(params):
+    """Pick the kernel instantiation from a decoder state dict (keys: SURVEY.md Appendix D)."""
+    w = params['base_net.0.weight']
+    if tuple(w.shape) == (64, 18) and 'dir_net.0.weight' in params and tuple(params['color_net.0.weight'].shape) == (3, 64):
+        return DEC_P
+    if tuple(w.shape) == (128, 96) and 'dir_net.0.weight' not in params \
+            and tuple(params['color_net.0.weight'].shape) == (128, 144) and 'color_net.2.weight' in params:
+        return DEC_S
+    raise N.SSDNeRFNativeError(
+        'unsupported TriPlaneDecoder shape: kernels exist for the shipped-config decoder (18->64, dir_net 16->64, 64->3) '
+        'and the class-default decoder (96->128, 144->128->3)')
+
+
+def _plane_major(w, C):
+    """columns of a Linear weight [out, 3*C] from the reference feature order c*3+plane to plane*C+c"""
+    out = w.shape[0]
+    return w.reshape(out, C, 3).permute(0, 2, 1).reshape(out, 3 * C)
+
+
+def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cuda'):
+    """Flatten decoder weights into the fp32 blob the kernels read (layout documented in csrc/render_fused.cu
+    `DecP` and csrc/render_tc.cu `DecS`)."""
+    if variant is None:
+        variant = detect_variant(params)
+    p = {k: v.detach().float().cpu() for k, v in params.items()}
+    if variant == DEC_P:
+        w1 = _plane_major(p['base_net.0.weight'], 6).t().contiguous()           # [18][64], row k = plane*6+c
+        parts = [w1.reshape(-1), p['base_net.0.bias'],
+                 p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),
+                 p['dir_net.0.weight'].t().contiguous().reshape(-1), p['dir_net.0.bias'],      # [16][64]
+                 p['color_net.0.weight'].reshape(-1), torch.cat([p['color_net.0.bias'], torch.zeros(1)]),
+                 torch.tensor([sigmoid_saturation, 0, 0, 0])]
+    elif variant == DEC_S:
+        w1 = _plane_major(p['base_net.0.weight'], 32)                             # [128][96] (N x K, K contiguous)
+        wc0 = p['color_net.0.weight']                                             # [128][144]: cols 0..127 base_act, 128..143 SH
+        parts = [w1.reshape(-1), p['base_net.0.bias'],
+                 p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),
+                 wc0.reshape(-1), p['color_net.0.bias'],
+                 p['color_net.2.weight'].reshape(-1), torch.cat([p['color_net.2.bias'], torch.zeros(1)]),
+                 torch.tensor([sigmoid_saturation, 0, 0, 0])]
+    else:
+        raise N.SSDNeRFNativeError(f'unknown decoder variant {variant}')
+    blob = torch.cat([x.float() for x in parts]).contiguous()
+    expect = N.lib().ssdnerf_decoder_blob_floats(N.c_int(variant))
+    if blob.numel() != expect:
+        raise N.SSDNeRFNativeError(f'decoder blob has {blob.numel()} floats, library expects {expect}')
+    return blob.to(device)
+
+
+def pack_planes(code, variant):
+    """code fp32 [B,3,C,H,W] (reference layout) -> channels-last gather layout (fp32 x8 for P, fp16 x32 for S)."""
+    N.require_cuda(code)
+    code = code.contiguous().float()
+    B, three, C, H, W = code.shape
+    assert three == 3
+    nbytes = N.lib().ssdnerf_planes_bytes(N.c_int(variant), N.c_u32(B), N.c_u32(H), N.c_u32(W))
+    planes = torch.empty(nbytes, dtype=torch.uint8, device=code.device)
+    N.check(N.lib().ssdnerf_pack_planes(N.c_int(variant), N.ptr(code), N.c_u32(B), N.c_u32(C), N.c_u32(H), N.c_u32(W),
+                                        N.ptr(planes), N.stream_ptr()))
+    return planes
+
+
+def render_fwd(variant, planes, plane_hw, bitfield, blob, rays_o=None, rays_d=None, poses=None, intrinsics=None,
+               img_hw=None, grid_size=64, bound=1.0, min_near=0.2, max_steps=256, T_thresh=1e-4, bg_color=1.0,
+               dt_gamma=None, emulate_schedule=True, trace_cap=0, want_blend=True, want_counts=True):
+    """One fused render of B scenes.
+
+    Either explicit rays (rays_o, rays_d: [B,N,3]) or cameras (poses [B,V,4,4], intrinsics [B,V,4], img_hw).
+    Returns dict(weights_sum [B,N], depth [B,N], image [B,N,3], rgb [B,N,3] (blended), num_samples [B,N] int32,
+    trace [B,N,trace_cap] int32)."""
+    N.require_cuda(planes, bitfield, blob)
+    dev = planes.device
+    if rays_o is not None:
+        rays_o = rays_o.contiguous().float()
+        rays_d = rays_d.contiguous().float()
+        B, n = rays_o.shape[0], rays_o.shape[1]
+        V = h = w = 0
+    else:
+        poses = poses.contiguous().float()
+        intrinsics = intrinsics.contiguous().float()
+        B, V = poses.shape[0], poses.shape[1]
+        h, w = img_hw
+        n = V * h * w
+        if tuple(poses.shape[-2:]) != (4, 4):
+            raise N.SSDNeRFNativeError('poses must be [B,V,4,4]')
+    bitfield = bitfield.contiguous()
+    if dt_gamma is not None:
+        dt_gamma = dt_gamma.contiguous().float().to(dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(weights_sum=torch.empty(B, n, **f32), depth=torch.empty(B, n, **f32), image=torch.empty(B, n, 3, **f32))
+    out['rgb'] = torch.empty(B, n, 3, **f32) if want_blend else None
+    out['num_samples'] = torch.empty(B, n, dtype=torch.int32, device=dev) if want_counts else None
+    out['trace'] = torch.empty(B, n, trace_cap, dtype=torch.int32, device=dev) if trace_cap > 0 else None
+    ws_bytes = N.lib().ssdnerf_render_workspace_bytes(N.c_u32(B), N.c_u32(n), N.c_u32(max_steps))
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    a = N.RenderArgs()
+    a.variant = variant
+    a.num_scenes, a.rays_per_scene = B, n
+    a.rays_o, a.rays_d = N.ptr(rays_o), N.ptr(rays_d)
+    a.poses, a.intrinsics = N.ptr(poses), N.ptr(intrinsics)
+    a.num_views, a.img_h, a.img_w = V, h, w
+    a.planes, a.plane_h, a.plane_w = N.ptr(planes), plane_hw[0], plane_hw[1]
+    a.bitfield, a.grid_size = N.ptr(bitfield), grid_size
+    a.decoder_blob, a.dt_gamma = N.ptr(blob), N.ptr(dt_gamma)
+    a.bound, a.min_near, a.T_thresh, a.bg_color = bound, min_near, T_thresh, bg_color
+    a.max_steps, a.emulate_schedule = max_steps, int(emulate_schedule)
+    a.weights_sum, a.depth, a.image = N.ptr(out['weights_sum']), N.ptr(out['depth']), N.ptr(out['image'])
+    a.rgb_blend, a.num_samples = N.ptr(out['rgb']), N.ptr(out['num_samples'])
+    a.voxel_trace, a.trace_cap = N.ptr(out['trace']), trace_cap
+    a.workspace, a.workspace_bytes = N.ptr(workspace), ws_bytes
+    import ctypes
+    N.check(N.lib().ssdnerf_render_fwd(ctypes.byref(a), N.stream_ptr()))
+    return out

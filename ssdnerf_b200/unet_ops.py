@@ -1,0 +1,144 @@
+"""Thin Python wrappers over the UNet building-block kernels (C ABI section 4, include/ssdnerf_b200.h).
+
+Activations are NHWC fp16 tensors; weights are packed once (`pack_conv_weight`, `pack_linear_weight`).
+"""
+import ctypes
+
+import torch
+
+from . import _lib as N
+
+c_u64 = ctypes.c_uint64
+c_ll = ctypes.c_longlong
+
+
+class GemmArgs(ctypes.Structure):
+    """mirror of `ssdnerf_gemm_args`"""
+    _fields_ = [
+        ('a1', N.c_void_p), ('a1_strides', c_u64 * 3), ('k1', N.c_u32),
+        ('a2', N.c_void_p), ('a2_strides', c_u64 * 3), ('k2', N.c_u32),
+        ('d1', N.c_u32), ('d2', N.c_u32), ('d3', N.c_u32), ('b1', N.c_u32), ('b2', N.c_u32), ('b3', N.c_u32),
+        ('taps', N.c_u32),
+        ('b', N.c_void_p), ('b_strides', c_u64 * 3), ('n', N.c_u32), ('n_rows_b', N.c_u32), ('bx2', N.c_u32), ('bx3', N.c_u32),
+        ('b_batched', N.c_u32),
+        ('bn', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
+        ('out', N.c_void_p), ('out_f32', N.c_u32), ('so1', c_ll), ('so2', c_ll), ('so3', c_ll),
+    ]
+
+
+def _launch(a):
+    N.check(N.lib().ssdnerf_gemm_f16(ctypes.byref(a), N.stream_ptr()))
+
+
+def _pad_rows(w, mult=64):
+    n = w.shape[-2]
+    pad = (-n) % mult
+    if pad:
+        w = torch.cat([w, w.new_zeros(*w.shape[:-2], pad, w.shape[-1])], dim=-2)
+    return w
+
+
+def pack_linear_weight(w):
+    """nn.Linear / 1x1-conv weight [N, K] -> fp16 [N_pad, K] (rows padded to a multiple of 64 so any N tile is in bounds)."""
+    w = w.detach().reshape(w.shape[0], -1).half()
+    assert w.shape[1] % 64 == 0, 'K must be a multiple of 64'
+    return _pad_rows(w).contiguous()
+
+
+def pack_conv_weight(w, cin_pad=None):
+    """Conv2d weight [Cout, Cin, 3, 3] -> fp16 [9][Cout_pad][Cin_pad] (tap = ky*3 + kx, K contiguous)."""
+    cout, cin = w.shape[0], w.shape[1]
+    cin_pad = cin_pad or ((cin + 63) // 64 * 64)
+    wp = w.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).half()
+    if cin_pad != cin:
+        wp = torch.cat([wp, wp.new_zeros(9, cout, cin_pad - cin)], dim=-1)
+    return _pad_rows(wp).contiguous()
+
+
+def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.0, bn=0, n=None):
+    """out[M, N] = alpha * a[M, K] @ w[N, K]^T + bias + residual.  a fp16 [M, K] (row stride may exceed K)."""
+    N.require_cuda(a, w)
+    M, K = a.shape
+    n = n if n is not None else w.shape[0]
+    if out is None:
+        out = torch.empty(M, n, dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
+    g = GemmArgs()
+    g.a1, g.k1 = a.data_ptr(), K
+    rs = a.stride(0) * 2
+    g.a1_strides = (c_u64 * 3)(rs, rs * M, rs * M)
+    g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = M, 1, 1, 128, 1, 1
+    g.taps = 1
+    g.b, g.n, g.n_rows_b, g.bx2, g.bx3 = w.data_ptr(), n, w.shape[0], 1, 1
+    ws = w.stride(0) * 2
+    g.b_strides = (c_u64 * 3)(ws, ws * w.shape[0], ws * w.shape[0])
+    g.bn, g.alpha = bn, alpha
+    g.bias_n = bias.data_ptr() if bias is not None else None
+    g.residual = residual.data_ptr() if residual is not None else None
+    g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)
+    g.so1, g.so2, g.so3 = out.stride(0), 0, 0
+    _launch(g)
+    return out
+
+
+def _conv_boxes(H, W):
+    bw = min(W, 128)
+    bh = min(H, 128 // bw)
+    nb = 128 // (bw * bh)
+    return bw, bh, nb
+
+
+def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0):
+    """3x3 (taps=9, pad 1, stride 1) or 1x1 (taps=1) convolution over NHWC fp16 x [B,H,W,C1] (+ x2 [B,H,W,C2] concatenated
+    along channels).  wp: packed weight [taps][Cout_pad][C1+C2]."""
+    N.require_cuda(x, wp)
+    B, H, W, C1 = x.shape
+    C2 = x2.shape[-1] if x2 is not None else 0
+    assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
+    assert wp.shape[-1] == C1 + C2 and C1 % 64 == 0 and C2 % 64 == 0, (wp.shape, C1, C2)
+    if out is None:
+        out = torch.empty(B, H, W, cout, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+    bw, bh, nb = _conv_boxes(H, W)
+    g = GemmArgs()
+    g.a1, g.k1 = x.data_ptr(), C1
+    g.a1_strides = (c_u64 * 3)(C1 * 2, W * C1 * 2, H * W * C1 * 2)
+    if x2 is not None:
+        g.a2, g.k2 = x2.data_ptr(), C2
+        g.a2_strides = (c_u64 * 3)(C2 * 2, W * C2 * 2, H * W * C2 * 2)
+    g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = W, H, B, bw, bh, nb
+    g.taps = taps
+    ktot = C1 + C2
+    rows = wp.shape[-2]
+    g.b, g.n, g.n_rows_b, g.bx2, g.bx3 = wp.data_ptr(), cout, rows, taps, 1
+    g.b_strides = (c_u64 * 3)(ktot * 2, rows * ktot * 2, taps * rows * ktot * 2)
+    g.bn, g.alpha = bn, 1.0
+    g.bias_n = bias.data_ptr() if bias is not None else None
+    g.residual = residual.data_ptr() if residual is not None else None
+    g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)
+    co = out.shape[-1]
+    g.so1, g.so2, g.so3 = co, W * co, H * W * co
+    _launch(g)
+    return out
+
+
+def attn_scores(qkv, heads, scale, out=None):
+    """S[b,h,t,s] = scale * q[b,t,h,:] . k[b,s,h,:] in fp32, q/k read in place from qkv [B,T,3c] with the reference's
+    legacy head layout (head h owns channels [h*3ch, (h+1)*3ch) = q | k | v; lib/models/architecture/ddpm/modules.py:36-48)."""
+    B, T, c3 = qkv.shape
+    c = c3 // 3
+    ch = c // heads
+    assert ch % 64 == 0
+    if out is None:
+        out = torch.empty(B, heads, T, T, dtype=torch.float32, device=qkv.device)
+    g = GemmArgs()
+    g.a1, g.k1 = qkv.data_ptr(), ch
+    g.a1_strides = (c_u64 * 3)(c3 * 2, 3 * ch * 2, T * c3 * 2)              # t, head, batch
+    g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = T, heads, B, 128, 1, 1
+    g.taps = 1
+    g.b = qkv.data_ptr() + ch * 2                                            # k slice of each head
+    g.n, g.n_rows_b, g.bx2, g.bx3, g.b_batched = T, T, heads, B, 1
+    g.b_strides = (c_u64 * 3)(c3 * 2, 3 * ch * 2, T * c3 * 2)
+    g.bn, g.alpha = 0, scale
+    g.out, g.out_f32 = out.data_ptr(), 1
+    g.so1, g.so2, g.so3 = T, T * T, heads * T * T
+    _launch(g)
+    return out

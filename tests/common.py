@@ -1,0 +1,50 @@
+"""Shared seeded inputs for the parity tests (SURVEY.md §8d config 1 and friends)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# demo/camera_spiral_cars/pose/000000.txt of the reference (the only real camera data available offline),
+# committed here because /root/reference does not exist on the GPU box.
+POSE0 = np.array([
+    -0.9129449725151062, -2.6523304086367716e-07, -0.40808194875717163, 0.5305066704750061,
+    0.40808194875717163, -4.6272722897811036e-07, -0.9129451513290405, 1.186828851699829,
+    1.2454208331291738e-07, -0.9999998807907104, 1.967826221971336e-07, 1.7763558229607138e-14,
+    -0.0, 0.0, -0.0, 1.0], dtype=np.float32).reshape(4, 4)
+
+
+def spiral_poses(num, radius=2.6, seed=0):
+    """Deterministic look-at cameras on a sphere of `radius` (stand-in for the 251-pose demo spiral)."""
+    poses = []
+    for i in range(num):
+        phi = 2 * np.pi * i / max(num, 1) + 0.3
+        theta = np.pi / 2 - 0.45 * np.sin(1.7 * phi)
+        pos = radius * np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+        fwd = -pos / np.linalg.norm(pos)
+        up = np.array([0.0, 0.0, 1.0])
+        right = np.cross(fwd, up); right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        c2w = np.eye(4)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, down, fwd, pos
+        poses.append(c2w)
+    return np.stack(poses).astype(np.float32)
+
+
+def config1(variant='S', seed=0, res=64):
+    """single random-init triplane, res x res render from the demo pose (translation x2), 32 samples/ray."""
+    g = torch.Generator().manual_seed(seed)
+    C = 32 if variant == 'S' else 6
+    code = torch.randn(1, 3, C, 128, 128, generator=g).clamp(-2, 2)
+    pose = POSE0.copy()
+    pose[:3, 3] *= 2
+    poses = torch.from_numpy(pose)[None, None]                      # [1,1,4,4]
+    f = 131.25 * res / 128
+    intr = torch.tensor([[[f, f, res / 2, res / 2]]], dtype=torch.float32)   # [1,1,4]
+    return code, poses, intr
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))

@@ -1,0 +1,68 @@
+"""tcgen05 GEMM / implicit-GEMM conv (C-ABI ssdnerf_gemm_f16) vs PyTorch fp32 on the same fp16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(out, ref, tol=2e-3):
+    err = (out.float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+    assert err < tol, f'rel err {err}'
+
+
+@pytest.mark.parametrize('M,N,K,bn', [(256, 128, 64, 128), (1000, 320, 192, 0), (128, 64, 128, 64), (4096, 512, 1024, 256)])
+def test_plain_gemm(cuda, M, N, K, bn):
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).half().to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.1).half().to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).half().to(cuda)
+    out = U.linear_f16(a, w, bias=bias, residual=res, bn=bn)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    _check(out, ref)
+    out32 = U.linear_f16(a, w, out_f32=True, alpha=0.25, bn=bn)
+    _check(out32, 0.25 * (a.float() @ w.float().t()), 1e-3)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 128, 128, 64, 128), (3, 64, 64, 128, 256), (2, 32, 32, 256, 256),
+                                            (3, 16, 16, 512, 512), (5, 8, 8, 512, 512)])
+def test_conv3x3(cuda, B, H, W, Cin, Cout):
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(B * H + Cin)
+    x = (torch.randn(B, H, W, Cin, generator=g)).half().to(cuda)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    wp = U.pack_conv_weight(w).to(cuda)
+    out = U.conv3x3_f16(x, wp, Cout, bias=b)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.half().float().to(cuda), b, padding=1).permute(0, 2, 3, 1)
+    _check(out, ref)
+
+
+def test_conv3x3_concat_and_residual(cuda):
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 32, 32
+    x1 = torch.randn(B, H, W, 256, generator=g).half().to(cuda)
+    x2 = torch.randn(B, H, W, 128, generator=g).half().to(cuda)
+    w = torch.randn(256, 384, 3, 3, generator=g) * 0.03
+    res = torch.randn(B, H, W, 256, generator=g).half().to(cuda)
+    out = U.conv3x3_f16(x1, U.pack_conv_weight(w).to(cuda), 256, x2=x2, residual=res)
+    xin = torch.cat([x1, x2], -1).float().permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xin, w.half().float().to(cuda), None, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref)
+
+
+def test_batched_attention_gemms(cuda):
+    """S = q k^T over (batch, head) with strided q/k slices of a [B,T,3c] qkv tensor (legacy head layout)."""
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(13)
+    B, T, c, heads = 2, 256, 256, 4
+    ch = c // heads
+    qkv = torch.randn(B, T, 3 * c, generator=g).half().to(cuda)
+    S = U.attn_scores(qkv, heads, scale=ch ** -0.5)
+    q = qkv.float().view(B, T, heads, 3, ch)[:, :, :, 0]
+    k = qkv.float().view(B, T, heads, 3, ch)[:, :, :, 1]
+    ref = torch.einsum('bthc,bshc->bhts', q, k) * ch ** -0.5
+    _check(S, ref, 1e-3)
