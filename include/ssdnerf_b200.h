@@ -22,15 +22,18 @@
 extern "C" {
 #endif
 
+/* exported symbols (the library is built with -fvisibility=hidden) */
+#define SSDNERF_API __attribute__((visibility("default")))
+
 #define SSDNERF_OK 0
 #define SSDNERF_ERR_CUDA (-1)   /* a CUDA runtime / driver call failed */
 #define SSDNERF_ERR_ARG (-2)    /* invalid argument (shape, alignment, unsupported variant) */
 #define SSDNERF_ERR_ARCH (-3)   /* device is not sm_100 */
 
-const char* ssdnerf_last_error(void);
+SSDNERF_API const char* ssdnerf_last_error(void);
 /* library version and the SM architecture it was compiled for (100) */
-int ssdnerf_version(void);
-int ssdnerf_compiled_arch(void);
+SSDNERF_API int ssdnerf_version(void);
+SSDNERF_API int ssdnerf_compiled_arch(void);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Legacy per-op entry points == the reference's pybind FFI, one to one.
@@ -40,41 +43,41 @@ int ssdnerf_compiled_arch(void);
  *    the reference's Python wrapper does, zero-fills) every output.
  * ---------------------------------------------------------------------------------------------- */
 /* replaces: near_far_from_aabb (raymarching.cu:148-156, kernel :92-145) */
-int ssdnerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+SSDNERF_API int ssdnerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
                                float* nears, float* fars, void* stream);
 /* replaces: sph_from_ray (raymarching.cu:200-208) -- unused by the model, kept for API completeness */
-int ssdnerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream);
+SSDNERF_API int ssdnerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream);
 /* replaces: morton3D / morton3D_invert (raymarching.cu:229-232, :257-260) */
-int ssdnerf_morton3D(const int* coords, uint32_t N, int* indices, void* stream);
-int ssdnerf_morton3D_invert(const int* indices, uint32_t N, int* coords, void* stream);
+SSDNERF_API int ssdnerf_morton3D(const int* coords, uint32_t N, int* indices, void* stream);
+SSDNERF_API int ssdnerf_morton3D_invert(const int* indices, uint32_t N, int* coords, void* stream);
 /* replaces: packbits (raymarching.cu:292-300); N = number of OUTPUT bytes; grid is fp32 or fp16 (grid_is_half) */
-int ssdnerf_packbits(const void* grid, int grid_is_half, uint32_t N, float thresh, uint8_t* bitfield, void* stream);
+SSDNERF_API int ssdnerf_packbits(const void* grid, int grid_is_half, uint32_t N, float thresh, uint8_t* bitfield, void* stream);
 /* replaces: march_rays_train (raymarching.cu:484-492, kernel :312-482); counter = int[2] {points, rays} */
-int ssdnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+SSDNERF_API int ssdnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                              const float* fars, float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
                              const float* noises, void* stream);
 /* replaces: composite_rays_train_forward / _backward (raymarching.cu:584-592, :690-698) */
-int ssdnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int* rays,
+SSDNERF_API int ssdnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int* rays,
                                          uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
                                          float* image, void* stream);
-int ssdnerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+SSDNERF_API int ssdnerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
                                           const float* rgbs, const float* deltas, const int* rays, const float* weights_sum,
                                           const float* image, uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
                                           float* grad_rgbs, void* stream);
 /* replaces: march_rays (raymarching.cu:815-822, kernel :706-812); noises may be NULL (== zeros) */
-int ssdnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
+SSDNERF_API int ssdnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
                        const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                        const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                        const float* noises, void* stream);
 /* replaces: composite_rays (raymarching.cu:916-922, kernel :826-913) */
-int ssdnerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive, float* rays_t,
+SSDNERF_API int ssdnerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive, float* rays_t,
                            const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
                            float* image, void* stream);
 /* replaces: sh_encode_forward / sh_encode_backward (shencoder.cu:386-399, :416-440); degree C <= 4 */
-int ssdnerf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t C, int calc_grad_inputs,
+SSDNERF_API int ssdnerf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t C, int calc_grad_inputs,
                               float* dy_dx, void* stream);
-int ssdnerf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t C, const float* dy_dx,
+SSDNERF_API int ssdnerf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t C, const float* dy_dx,
                                float* grad_inputs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -94,13 +97,13 @@ int ssdnerf_sh_encode_backward(const float* grad, const float* inputs, uint32_t 
                            (lib/models/decoders/triplane_decoder.py:24-39) */
 
 /* Size in floats of the packed fp32 decoder-weight blob for a variant (layout: ssdnerf_b200/decoder_pack.py). */
-size_t ssdnerf_decoder_blob_floats(int variant);
+SSDNERF_API size_t ssdnerf_decoder_blob_floats(int variant);
 
 /* Re-layout one batch of triplanes for the gather:
  *   code  fp32 [B][3][C][Hp][Wp]  (reference layout, triplane_decoder.py:123)
  *   -> planes [B][3][Hp][Wp][Cpad] channels-last, fp32 (variant P, Cpad = 8) or fp16 (variant S, Cpad = 32). */
-size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp);
-int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, uint32_t Hp, uint32_t Wp, void* planes,
+SSDNERF_API size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp);
+SSDNERF_API int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, uint32_t Hp, uint32_t Wp, void* planes,
                         void* stream);
 
 typedef struct ssdnerf_render_args {
@@ -138,8 +141,8 @@ typedef struct ssdnerf_render_args {
     size_t workspace_bytes;
 } ssdnerf_render_args;
 
-size_t ssdnerf_render_workspace_bytes(uint32_t num_scenes, uint32_t rays_per_scene, uint32_t max_steps);
-int ssdnerf_render_fwd(const ssdnerf_render_args* args, void* stream);
+SSDNERF_API size_t ssdnerf_render_workspace_bytes(uint32_t num_scenes, uint32_t rays_per_scene, uint32_t max_steps);
+SSDNERF_API int ssdnerf_render_fwd(const ssdnerf_render_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. Occupancy-grid builder.
@@ -148,13 +151,13 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* args, void* stream);
  *    Two launches per iteration: ssdnerf_density_update (decode + max + per-block partial sums) then
  *    ssdnerf_density_pack (threshold = min(mean, density_thresh), bit pack).  No host sync.
  * ---------------------------------------------------------------------------------------------- */
-size_t ssdnerf_density_workspace_bytes(uint32_t num_scenes, uint32_t grid_size);
-int ssdnerf_density_update(int variant, const void* planes, uint32_t plane_h, uint32_t plane_w, const float* decoder_blob,
+SSDNERF_API size_t ssdnerf_density_workspace_bytes(uint32_t num_scenes, uint32_t grid_size);
+SSDNERF_API int ssdnerf_density_update(int variant, const void* planes, uint32_t plane_h, uint32_t plane_w, const float* decoder_blob,
                            uint32_t num_scenes, uint32_t grid_size, float bound,
                            const float* jitter,   /* [G^3][3] uniform [0,1) in ij-meshgrid order (== torch.rand_like of
                                                      base_nerf.py:344), shared by all scenes; NULL = voxel centres */
                            float decay, void* density_grid, int grid_is_half, void* workspace, void* stream);
-int ssdnerf_density_pack(const void* density_grid, int grid_is_half, uint32_t num_scenes, uint32_t grid_size,
+SSDNERF_API int ssdnerf_density_pack(const void* density_grid, int grid_is_half, uint32_t num_scenes, uint32_t grid_size,
                          float density_thresh, uint8_t* bitfield, float* thresh_out /* [1], optional */,
                          void* workspace, void* stream);
 
@@ -185,7 +188,7 @@ typedef struct ssdnerf_gemm_args {
     const void* residual;     /* fp16, addressed like out, or NULL */
     void* out; uint32_t out_f32; long long so1, so2, so3; /* element strides of d1, d2, d3; columns contiguous */
 } ssdnerf_gemm_args;
-int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
+SSDNERF_API int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ struct RenderParams {
     uint32_t* counters;        // [0] main-pass tile counter, [1] fix-up tile counter
     uint32_t* hist; uint32_t hist_bins;
     uint32_t* budget;          // [B] emulated per-ray sample budget
-    uint32_t hard_cap;
+    uint32_t hard_cap, max_steps;
     int patch_tiles;           // camera mode: a 32-ray tile is an 8x4 pixel patch instead of 32 consecutive pixels
 };
 
