@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- SSDNeRF hot-path benchmark (contract: see the task brief; numbers explained in DESIGN.md §6).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a kernels
+    python bench.py --impl reference --steps K --warmup W    # reference arithmetic on the host cores (oracle port)
+
+Workload (BASELINE.json configs[1]): `ssdnerf_cars_uncond`, batch 16 scenes per GPU, one STEP =
+    50-step DDIM sample of a (3,6,128,128) triplane batch  ->  8-iteration occupancy-grid build  ->
+    251-view 128x128 render of every scene (4.1 M rays per scene),
+random-init weights of the shipped architecture (UNet convs re-drawn N(0, 0.02) because the reference zero-inits
+half of them), synthetic noise and a synthetic 251-pose camera orbit.  Scenes are independent, so N GPUs run N
+independent batches (weak scaling, no data-path collective; the only exchange is the eval-side image all-gather).
+
+`value`   = rays/s of the render stage, inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+`triplanes_per_sec` = batch / DDIM-stage time, same measurement
+`e2e`     = the same step through the public plugin API (`DiffusionNeRF.val_step`) with PINNED HOST inputs and a
+            device->host read of the rendered images inside the timed region; e2e.value = rays / whole-step time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 16
+NUM_VIEWS = 251
+IMG = 128
+DDIM_STEPS = 50
+METRIC = 'rays/sec (128^2 render) & DDIM triplanes/sec'
+UNET_FLOP_PER_SAMPLE_STEP = 217.96e9
+RAY_GATHER_BYTES_PER_SAMPLE = 288        # 3 planes x 4 taps x 6 ch x fp32
+RAY_IO_BYTES = 20                        # image[3] + depth + weights_sum per ray
+
+
+def orbit_poses(num, radius=2.6):
+    """synthetic stand-in for demo/camera_spiral_cars (251 poses at radius 1.3 x 2): look-at cameras on a sphere"""
+    poses = []
+    for i in range(num):
+        phi = 2 * np.pi * i / num + 0.3
+        theta = np.pi / 2 - 0.45 * np.sin(1.7 * phi)
+        pos = radius * np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+        fwd = -pos / np.linalg.norm(pos)
+        right = np.cross(fwd, np.array([0.0, 0.0, 1.0])); right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        c2w = np.eye(4)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, down, fwd, pos
+        poses.append(c2w)
+    return torch.from_numpy(np.stack(poses).astype(np.float32))
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']), src='measured')
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------- this repo
+def build_model(dev, seed=0):
+    import ssdnerf_b200 as S
+    cfg = S.Config.fromfile(os.path.join(ROOT, 'configs', 'cars_uncond_b200.py'))
+    torch.manual_seed(seed)
+    model = S.build_model(cfg.model, test_cfg=cfg.test_cfg)
+    g = torch.Generator().manual_seed(seed)
+    for mod in (model.diffusion_ema.denoising, model.diffusion.denoising):
+        for name, p in mod.named_parameters():
+            if p.dim() > 1:
+                p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)     # non-degenerate UNet
+    return model.to(dev).eval(), cfg
+
+
+def run_ours(args):
+    import ssdnerf_b200 as S
+    from ssdnerf_b200 import _lib as N
+    from ssdnerf_b200 import renderer as R
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    model, cfg = build_model(dev, seed=0)
+    diffusion, decoder = model.diffusion_ema, model.decoder_ema
+    B, V = args.batch, args.views
+    g = torch.Generator().manual_seed(1234 + rank)
+    noise_host = torch.randn(B, *model.code_size, generator=g).pin_memory()
+    poses_host = orbit_poses(V)[None].repeat(B, 1, 1, 1).contiguous().pin_memory()
+    intr_host = torch.tensor([131.25, 131.25, 64.0, 64.0]).expand(B, V, 4).contiguous().pin_memory()
+    rays = B * V * IMG * IMG
+    L = N.lib()
+    L.ssdnerf_launch_count.restype = __import__('ctypes').c_ulonglong
+
+    noise, poses, intr = noise_host.to(dev), poses_host.to(dev), intr_host.to(dev)
+    stream = torch.cuda.current_stream(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def resident_step(rec=None):
+        """one step with inputs already in HBM; stage boundaries marked with CUDA events on the launching stream"""
+        e = [ev() for _ in range(4)]
+        e[0].record(stream)
+        code = model.code_diff_pr_inv(diffusion(model.code_diff_pr(noise), return_loss=False)).contiguous()
+        e[1].record(stream)
+        grid, bitfield = model.get_density(decoder, code, cfg=model.test_cfg)
+        e[2].record(stream)
+        img, depth = model.render(decoder, code, bitfield, IMG, IMG, intr, poses, cfg=model.test_cfg)
+        e[3].record(stream)
+        if rec is not None:
+            rec.append(e)
+        return img
+
+    out_host = torch.empty(B, V, 3, IMG, IMG, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        """public API with host buffers: H2D inputs, val_step, D2H of the rendered images (lib/apis/test.py:27-53 data flow)"""
+        data = dict(scene_id=list(range(B)), scene_name=[str(i) for i in range(B)], noise=noise_host.to(dev, non_blocking=True),
+                    test_poses=poses_host.to(dev, non_blocking=True), test_intrinsics=intr_host.to(dev, non_blocking=True))
+        out = model.val_step(data)
+        out_host.copy_(out['pred_imgs'], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- resident (kernel-side) measurement
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    launches0 = L.ssdnerf_launch_count()
+    replays_per_step = DDIM_STEPS
+    clocks = ClockSampler(local); clocks.start()
+    rec = []
+    t0, t1 = ev(), ev()
+    t0.record(stream)
+    for _ in range(args.steps):
+        resident_step(rec)
+    t1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    total_ms = t0.elapsed_time(t1) / args.steps
+    ddim_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in rec]))
+    dens_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in rec]))
+    rend_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in rec]))
+    launches_api = (L.ssdnerf_launch_count() - launches0) / args.steps
+    # kernels inside the replayed CUDA graph are launched by the driver: count the graph's kernel nodes once per replay
+    graph_nodes = getattr(diffusion, '_graph_kernel_nodes', 0)
+    gpu_launches = int(launches_api + graph_nodes * (replays_per_step - 1))
+
+    # ---- end-to-end through the plugin API with host buffers
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    s0, s1 = ev(), ev()
+    s0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    s1.record(stream)
+    barrier()
+    e2e_ms = s0.elapsed_time(s1) / args.steps
+
+    # ---- sample statistics of the render workload (one extra untimed launch with counts)
+    code = model.code_diff_pr_inv(diffusion(model.code_diff_pr(noise), return_loss=False)).contiguous()
+    _, bitfield = model.get_density(decoder, code, cfg=model.test_cfg)
+    variant = decoder.fused_variant()
+    cnt = R.render_fwd(variant, R.pack_planes(code, variant), (128, 128), bitfield, decoder.packed_blob(), poses=poses, intrinsics=intr,
+                       img_hw=(IMG, IMG), want_blend=False)['num_samples']
+    samples = int(cnt.sum().item())
+
+    # ---- reduce over ranks (max time)
+    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms], device=dev, dtype=torch.float64)
+    samples_t = torch.tensor([samples], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(samples_t, op=dist.ReduceOp.SUM)
+    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms = [float(x) for x in times.tolist()]
+    samples_all = float(samples_t.item())
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    rays_all, trip_all = rays * world, B * world
+    rays_per_s = rays_all / (rend_ms * 1e-3)
+    trip_per_s = trip_all / (ddim_ms * 1e-3)
+    # roofline of the dominant kernel of the step (the DDIM stage is > 80 % of the step): tcgen05 implicit-GEMM conv
+    unet_flops = UNET_FLOP_PER_SAMPLE_STEP * B * DDIM_STEPS            # per rank per step
+    tf_achieved = unet_flops / (ddim_ms * 1e-3) / 1e12
+    render_bytes = (samples_all / world) * RAY_GATHER_BYTES_PER_SAMPLE + rays * RAY_IO_BYTES
+    line = {
+        'metric': METRIC, 'value': rays_per_s, 'unit': 'rays/s', 'triplanes_per_sec': trip_per_s,
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp16 tensor-core UNet (fp32 accumulate), fp32 renderer', 'data': 'synthetic',
+        'config': {'workload': f'ssdnerf_cars_uncond: {DDIM_STEPS}-step DDIM + 8-iter density grid + {V}-view {IMG}x{IMG} render, '
+                               f'batch {B}/GPU', 'global_batch': trip_all, 'rays_per_step': rays_all, 'samples_per_ray': samples_all / rays_all,
+                   'parallelism': f'scenes x{world} (independent replicas, no data-path collective)',
+                   'l2_policy': 'working set per step (activations > 1 GB, 66 M rays of output) exceeds the 126 MB L2; no flush needed'},
+        'stage_ms': {'ddim': ddim_ms, 'density': dens_ms, 'render': rend_ms},
+        'e2e': {'value': rays_all / (e2e_ms * 1e-3), 'unit': 'rays/s (whole val_step: H2D + DDIM + density + render + D2H)',
+                'triplanes_per_sec': trip_all / (e2e_ms * 1e-3), 'ms_per_step': e2e_ms,
+                'h2d_bytes_per_step': int(noise_host.numel() * 4 + poses_host.numel() * 4 + intr_host.numel() * 4),
+                'd2h_bytes_per_step': int(out_host.numel() * 4)},
+        'gpu_launches': gpu_launches,
+        'clocks': clk,
+        'roofline': {'kernel': 'k_gemm_tc (tcgen05 implicit-GEMM conv / GEMM of the UNet), timed as the whole DDIM stage',
+                     'bound': 'tensor', 'achieved': tf_achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                     'frac': tf_achieved / pk['tf_sustained'], 'peak_source': f"{pk['src']} (sustained cuBLAS bf16)", 'traffic': None},
+        'roofline_render': {'kernel': 'k_render_p', 'bound': 'hbm', 'achieved': render_bytes / (rend_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'],
+                            'unit': 'GB/s', 'frac': render_bytes / (rend_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'peak_source': pk['src'],
+                            'note': 'algorithmic gather bytes; the 1.5 MB/scene planes are L2-resident, so this is an L2-side figure'},
+    }
+    if args.cpu_baseline:
+        line['cpu_baseline'] = cpu_reference_sample(quick=True)
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_sample(quick=False, unet_evals=4, views=4):
+    """Reference arithmetic on the host cores = the oracle port (PyTorch-CPU UNet + C marcher/compositor + PyTorch-CPU decode);
+    the reference itself has no CPU path for the renderer. Bounded sample of the bench workload:
+    B=1 scene, `unet_evals` UNet evaluations (extrapolated x50/`unet_evals`), `views` 128x128 views."""
+    from oracle import render_port as rp
+    from oracle import unet_port as up
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if quick:
+        unet_evals, views = 2, 1
+    spec = up.unet_spec()
+    sd = up.random_state_dict(spec, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 18, 128, 128, generator=g)
+    t = torch.tensor([999])
+    with torch.no_grad():
+        up.unet_forward(sd, spec, x, t)                 # warm-up
+        t0 = time.perf_counter()
+        for _ in range(unet_evals):
+            v = up.unet_forward(sd, spec, x, t)
+        t_unet = (time.perf_counter() - t0) / unet_evals
+    params = rp.make_decoder_params('P', 0, nonzero_dir=False)
+    code = torch.randn(1, 3, 6, 128, 128, generator=g).clamp(-2, 2)
+    rands = [torch.rand(64 ** 3, 3, generator=g)]
+    _, bf = rp.get_density(params, code, rands, density_thresh=0.1)
+    poses = orbit_poses(NUM_VIEWS)[:views]
+    intr = torch.tensor([131.25, 131.25, 64.0, 64.0]).expand(views, 4).contiguous()
+    t0 = time.perf_counter()
+    rp.render_image(params, code[0], bf[0], poses, intr, IMG, IMG, max_steps=256)
+    t_render = time.perf_counter() - t0
+    rays = views * IMG * IMG
+    return {'value': rays / t_render, 'unit': 'rays/s', 'triplanes_per_sec': 1.0 / (t_unet * DDIM_STEPS), 'cores': cores, 'kind': 'port',
+            'sample': f'B=1: {unet_evals} UNet evaluations (fp32, {t_unet:.3f} s each, x{DDIM_STEPS} extrapolated) + {views} view(s) '
+                      f'{IMG}x{IMG} through the oracle host loop ({t_render:.2f} s)',
+            'unet_s_per_eval': t_unet, 'render_s': t_render}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    vals, trips, t_all = [], [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = cpu_reference_sample(unet_evals=3, views=2)
+        if i >= args.warmup:
+            vals.append(r['value']); trips.append(r['triplanes_per_sec']); t_all.append(time.perf_counter() - t0)
+    v, tr = float(np.mean(vals)), float(np.mean(trips))
+    r['value'] = v
+    r['triplanes_per_sec'] = tr
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'rays/s', 'triplanes_per_sec': tr, 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(t_all)) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': f'ssdnerf_cars_uncond: {DDIM_STEPS}-step DDIM + {IMG}x{IMG} render, bounded CPU sample of the same workload (see cpu_baseline.sample)'},
+            'cpu_baseline': r, 'e2e': {'value': v, 'unit': 'rays/s', 'triplanes_per_sec': tr, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=B_PER_GPU)
+    ap.add_argument('--views', type=int, default=NUM_VIEWS)
+    ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'b200':
+        args.warmup = 3      # timing rule: at least 3 warm-up steps
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

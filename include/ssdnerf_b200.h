@@ -34,6 +34,8 @@ SSDNERF_API const char* ssdnerf_last_error(void);
 /* library version and the SM architecture it was compiled for (100) */
 SSDNERF_API int ssdnerf_version(void);
 SSDNERF_API int ssdnerf_compiled_arch(void);
+/* number of CUDA kernels this library has launched (or recorded into a capturing stream) in this process */
+SSDNERF_API unsigned long long ssdnerf_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Legacy per-op entry points == the reference's pybind FFI, one to one.
@@ -189,6 +191,36 @@ typedef struct ssdnerf_gemm_args {
     void* out; uint32_t out_f32; long long so1, so2, so3; /* element strides of d1, d2, d3; columns contiguous */
 } ssdnerf_gemm_args;
 SSDNERF_API int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
+
+/* x fp32 [B,C,H,W] -> fp16 [B,H,W,Cpad] (zero-padded channels): UNet input layout */
+SSDNERF_API int ssdnerf_nchw_to_nhwc_f16(const float* x, uint32_t B, uint32_t C, uint32_t H, uint32_t W, uint32_t Cpad, void* out, void* stream);
+/* GroupNorm over the channel concat of x1 [B,HW,C1] and optional x2 [B,HW,C2] (fp16 NHWC):
+ * stats [B][groups][2] += {sum, sum of squares} (caller zero-fills); apply: y = GN(x)*gamma+beta, optionally
+ * y = y*(1+scale)+shift with scale_shift = [scale(C) | shift(C)] per sample (NormWithEmbedding, use_scale_shift_norm)
+ * and SiLU; writes the concatenated fp16 result. */
+SSDNERF_API int ssdnerf_gn_stats(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups,
+                                 float* stats, void* stream);
+SSDNERF_API int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups,
+                                 const float* stats, const float* gamma, const float* beta, const float* scale_shift,
+                                 long long ss_batch_stride, float eps, int do_silu, void* out, void* stream);
+/* [B,H,W,C] -> [B,H/2,W/2,9C] patches of a 3x3 stride-2 pad-1 convolution (DenoisingDownsample), K index = tap*C + c */
+SSDNERF_API int ssdnerf_im2col_s2(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream);
+/* nearest-neighbour x2 (DenoisingUpsample) */
+SSDNERF_API int ssdnerf_upsample2x(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream);
+/* P = softmax(S) along the last axis; S fp32 [rows][T] -> P fp16 */
+SSDNERF_API int ssdnerf_softmax_rows(const float* S, uint32_t rows, uint32_t T, void* P, void* stream);
+/* Vt[b][h][c][t] = qkv[b][t][h*3ch + 2ch + c] (legacy head layout of modules.py:36-48) */
+SSDNERF_API int ssdnerf_transpose_v(const void* qkv, uint32_t B, uint32_t T, uint32_t heads, uint32_t ch, void* vt, void* stream);
+/* One DDIM step of the V-parameterisation (gaussian_diffusion.py:198-230,264-293), x_t fp32 [B,C,H,W] updated in place:
+ *   x0 = clamp(c0*x_t - c1*v);  eps = (x_t - c0*x0)/c1;  x_prev = c2*x0 + c3*eps,  coef[step] = {c0,c1,c2,c3}
+ * v fp32 NHWC [B,H,W,Cv]; step index read from *step_ptr (device) or 0; optionally writes x0 and the next UNet input. */
+SSDNERF_API int ssdnerf_ddim_update(float* x_t, const float* v, uint32_t B, uint32_t C, uint32_t H, uint32_t W, uint32_t Cv,
+                                    const float* coef, const int* step_ptr, int clip, float clip_lo, float clip_hi, float* x0_out,
+                                    void* next_in, uint32_t Cpad, void* stream);
+/* device-side step bookkeeping of the graph-replayed DDIM loop: *step_ptr = value (set) or += value; and
+ * dst[c][:] = table[*step_ptr][:] for c < copies (selects the per-step time-embedding projections) */
+SSDNERF_API int ssdnerf_step_counter(int* step_ptr, int value, int set, void* stream);
+SSDNERF_API int ssdnerf_select_row(const float* table, uint32_t row_elems, const int* step_ptr, float* dst, uint32_t copies, void* stream);
 
 #ifdef __cplusplus
 }

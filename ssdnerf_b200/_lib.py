@@ -16,6 +16,7 @@ c_u32 = ctypes.c_uint32
 c_f32 = ctypes.c_float
 c_int = ctypes.c_int
 c_size_t = ctypes.c_size_t
+c_longlong = ctypes.c_longlong
 
 
 class SSDNeRFNativeError(RuntimeError):

@@ -20,6 +20,14 @@ constexpr float kSqrt3 = 1.7320508075688772f;
         if (_e != cudaSuccess) return ssdnerf::set_error(_e, #call, __FILE__, __LINE__); \
     } while (0)
 
+// every kernel launch site: count it (ssdnerf_launch_count) and surface launch errors
+#define SSDNERF_LAUNCH_OK()                          \
+    do {                                             \
+        ssdnerf::count_launch();                     \
+        SSDNERF_CUDA_OK(cudaGetLastError());         \
+    } while (0)
+
+void count_launch();
 int set_error(cudaError_t e, const char* what, const char* file, int line);
 int set_error_msg(int code, const char* msg);
 

@@ -184,7 +184,7 @@ int ssdnerf_density_update(int variant, const void* planes, uint32_t plane_h, ui
     else
         k_density_update_p<float><<<blocks, kDenThreads, 0, stream>>>((const float*)planes, plane_h, plane_w, decoder_blob, num_scenes,
                                                                       grid_size, bound, jitter, decay, (float*)density_grid, partials);
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     return 0;
 }
 
@@ -198,11 +198,11 @@ int ssdnerf_density_pack(const void* density_grid, int grid_is_half, uint32_t nu
     float* thresh = reinterpret_cast<float*>(workspace);
     const float* partials = reinterpret_cast<const float*>((unsigned char*)workspace + 16);
     k_density_thresh<<<1, 1024, 0, stream>>>(partials, blocks, (float)total, density_thresh, grid_is_half, thresh, thresh_out);
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     const uint32_t nbytes = (uint32_t)(total / 8);
     if (grid_is_half) k_density_pack<__half><<<div_up(nbytes, 256u), 256, 0, stream>>>((const __half*)density_grid, nbytes, thresh, bitfield);
     else k_density_pack<float><<<div_up(nbytes, 256u), 256, 0, stream>>>((const float*)density_grid, nbytes, thresh, bitfield);
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     return 0;
 }
 

@@ -260,7 +260,7 @@ static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUt
     const uint32_t total = p.T1 * p.T2 * p.T3 * p.tiles_n;
     const uint32_t grid = total < (uint32_t)sms ? total : (uint32_t)sms;
     k_gemm_tc<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(mA1, mA2, mB, p);
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     return 0;
 }
 

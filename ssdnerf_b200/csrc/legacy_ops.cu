@@ -299,7 +299,7 @@ using namespace ssdnerf;
     do {                                                                                    \
         if ((N) > 0) {                                                                      \
             kernel<<<div_up((uint32_t)(N), kThreads), kThreads, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__); \
-            SSDNERF_CUDA_OK(cudaGetLastError());                                            \
+            SSDNERF_LAUNCH_OK();                                            \
         }                                                                                   \
     } while (0)
 

@@ -248,7 +248,7 @@ __global__ void k_schedule(const uint32_t* __restrict__ hist, uint32_t hist_bins
 int launch_schedule(const uint32_t* hist, uint32_t hist_bins, uint32_t num_scenes, uint32_t N, uint32_t max_steps,
                     uint32_t* budget, cudaStream_t stream) {
     k_schedule<<<div_up(num_scenes, 64u), 64, 0, stream>>>(hist, hist_bins, num_scenes, N, max_steps, budget);
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     return 0;
 }
 
@@ -286,7 +286,7 @@ int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, 
     } else {
         return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: unknown decoder variant");
     }
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     return 0;
 }
 
@@ -359,11 +359,11 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
         const uint32_t total_tiles = div_up(a->rays_per_scene, 32u) * a->num_scenes;
         const uint32_t grid = (uint32_t)min((uint64_t)sms * occ, (uint64_t)div_up(total_tiles, kWarpsPerCta));
         k_render_p<<<grid, kCtaThreads, smem, stream>>>(p, 0);
-        SSDNERF_CUDA_OK(cudaGetLastError());
+        SSDNERF_LAUNCH_OK();
         if (a->emulate_schedule) {
             if (int e = launch_schedule(hist, p.hist_bins, a->num_scenes, a->rays_per_scene, a->max_steps, p.budget, stream)) return e;
             k_render_p<<<grid, kCtaThreads, smem, stream>>>(p, 1);
-            SSDNERF_CUDA_OK(cudaGetLastError());
+            SSDNERF_LAUNCH_OK();
         }
         return 0;
     }

@@ -351,11 +351,11 @@ int render_s_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist,
     const uint32_t total_tiles = div_up(div_up(p.rays_per_scene, 32u), 4u) * p.num_scenes;
     const uint32_t grid = (uint32_t)min((uint64_t)sms * occ, (uint64_t)total_tiles);
     k_render_s<<<grid, kSThreads, smem, stream>>>(p, 0);
-    SSDNERF_CUDA_OK(cudaGetLastError());
+    SSDNERF_LAUNCH_OK();
     if (emulate_schedule) {
         if (int e = launch_schedule(hist, p.hist_bins, p.num_scenes, p.rays_per_scene, p.max_steps, p.budget, stream)) return e;
         k_render_s<<<grid, kSThreads, smem, stream>>>(p, 1);
-        SSDNERF_CUDA_OK(cudaGetLastError());
+        SSDNERF_LAUNCH_OK();
     }
     return 0;
 }

@@ -1,0 +1,233 @@
+"""`VolumeRenderer` / `TriPlaneDecoder` -- the reference's decoder plugin, backed by the fused sm_100a renderer.
+
+Plugin surface of lib/models/decoders/base_volume_renderer.py:11-133 and triplane_decoder.py:15-184: registered name
+`TriPlaneDecoder`, constructor kwargs, state-dict keys (`aabb`, `base_net.0.*`, `density_net.0.*`, `dir_net.0.*`,
+`color_net.{0,2}.*`), `forward(rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh,
+return_loss)` returning `dict(weights_sum, depth, image)` as per-scene lists in eval mode, `point_decode`,
+`point_density_decode`, attributes `bound / min_near / max_steps / aabb`.
+
+eval mode (`self.training == False`): ONE fused launch sequence (csrc/render_fused.cu, csrc/render_tc.cu).
+train mode: the reference's op-by-op composition on the per-op kernels of this library (march_rays_train ->
+point_decode -> composite_rays_train with analytic backward) so autograd through the renderer keeps working.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as N
+from . import renderer as R
+from .activation import TruncExp
+from .raymarching import batch_composite_rays_train, batch_near_far_from_aabb, march_rays_train
+from .registry import MODULES, build_module
+from .shencoder import SHEncoder
+
+
+class VolumeRenderer(nn.Module):
+    def __init__(self, bound=1, min_near=0.2, bg_radius=-1, max_steps=256, decoder_reg_loss=None):
+        super().__init__()
+        self.bound = bound
+        self.min_near = min_near
+        self.bg_radius = bg_radius
+        self.max_steps = max_steps
+        self.decoder_reg_loss = build_module(decoder_reg_loss) if decoder_reg_loss is not None else None
+        self.register_buffer('aabb', torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound]))
+
+    def point_decode(self, xyzs, dirs, code):
+        raise NotImplementedError
+
+    def point_density_decode(self, xyzs, code):
+        raise NotImplementedError
+
+    def loss(self):
+        assert self.decoder_reg_loss is None
+        return None
+
+
+def _xavier_uniform_(m):
+    nn.init.xavier_uniform_(m.weight, gain=1)
+    nn.init.constant_(m.bias, 0)
+
+
+@MODULES.register_module()
+class TriPlaneDecoder(VolumeRenderer):
+    activation_dict = {'relu': nn.ReLU, 'silu': nn.SiLU, 'softplus': nn.Softplus, 'trunc_exp': TruncExp}
+
+    def __init__(self, *args, interp_mode='bilinear', base_layers=[3 * 32, 128], density_layers=[128, 1],
+                 color_layers=[128, 128, 3], use_dir_enc=True, dir_layers=None, scene_base_size=None, scene_rand_dims=(0, 1),
+                 activation='silu', sigma_activation='trunc_exp', sigmoid_saturation=0.001, code_dropout=0.0, flip_z=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        color_layers = list(color_layers)
+        self.interp_mode = interp_mode
+        self.in_chn = base_layers[0]
+        self.use_dir_enc = use_dir_enc
+        self.scene_base = None
+        if scene_base_size is not None:
+            raise NotImplementedError('scene_base is unused by every reference config and not built')
+        self.dir_encoder = SHEncoder() if use_dir_enc else None
+        self.sigmoid_saturation = sigmoid_saturation
+        act = self.activation_dict[activation.lower()]
+
+        def mlp(layers, last=None):
+            mods = []
+            for i in range(len(layers) - 1):
+                mods.append(nn.Linear(layers[i], layers[i + 1]))
+                if i != len(layers) - 2:
+                    mods.append(act())
+            if last is not None:
+                mods.append(last)
+            return nn.Sequential(*mods)
+
+        self.base_net = mlp(base_layers)
+        self.base_activation = act()
+        self.density_net = mlp(density_layers, self.activation_dict[sigma_activation.lower()]())
+        self.dir_net = None
+        if use_dir_enc:
+            if dir_layers is not None:
+                self.dir_net = mlp(dir_layers)
+            else:
+                color_layers[0] = color_layers[0] + 16
+        self.color_net = mlp(color_layers, nn.Sigmoid())
+        self.code_dropout = nn.Dropout2d(code_dropout) if code_dropout > 0 else None
+        self.flip_z = flip_z
+        self._fused_cfg = dict(interp_mode=interp_mode, activation=activation.lower(), sigma_activation=sigma_activation.lower(),
+                               use_dir_enc=use_dir_enc, flip_z=flip_z, code_dropout=code_dropout)
+        self._blob = None
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                _xavier_uniform_(m)
+        if self.dir_net is not None:
+            nn.init.constant_(self.dir_net[-1].weight, 0)
+            nn.init.constant_(self.dir_net[-1].bias, 0)
+
+    # ------------------------------------------------------------------ fused path helpers
+    def decoder_params(self):
+        keys = ['base_net.0', 'density_net.0', 'color_net.0'] + (['dir_net.0'] if self.dir_net is not None else []) \
+            + (['color_net.2'] if len([m for m in self.color_net if isinstance(m, nn.Linear)]) > 1 else [])
+        sd = self.state_dict()
+        return {k + s: sd[k + s] for k in keys for s in ('.weight', '.bias')}
+
+    def fused_variant(self):
+        c = self._fused_cfg
+        if not (c['interp_mode'] == 'bilinear' and c['activation'] == 'silu' and c['sigma_activation'] == 'trunc_exp'
+                and c['use_dir_enc'] and not c['flip_z']):
+            raise N.SSDNeRFNativeError('fused renderer covers bilinear / SiLU / trunc_exp / SH-encoded decoders (every reference config)')
+        return R.detect_variant(self.decoder_params())
+
+    def packed_blob(self):
+        key = tuple(p._version for p in self.parameters()) + (str(self.aabb.device),)
+        if self._blob is None or self._blob[0] != key:
+            self._blob = (key, R.pack_decoder_blob(self.decoder_params(), self.fused_variant(), self.sigmoid_saturation, self.aabb.device))
+        return self._blob[1]
+
+    # ------------------------------------------------------------------ reference API: point decode (module path)
+    def xyz_transform(self, xyz):
+        if self.flip_z:
+            xyz = torch.cat([xyz[..., :2], -xyz[..., 2:]], dim=-1)
+        xy, xz, yz = xyz[..., :2], xyz[..., ::2], xyz[..., 1:]
+        if xyz.dim() == 2:
+            return torch.stack([xy, xz, yz], dim=0).unsqueeze(1)
+        if xyz.dim() == 3:
+            num_scenes, num_points, _ = xyz.size()
+            return torch.stack([xy, xz, yz], dim=1).reshape(num_scenes * 3, 1, num_points, 2)
+        raise ValueError
+
+    def point_decode(self, xyzs, dirs, code, density_only=False):
+        """triplane_decoder.py:119-179 (differentiable module path used by the train branch and by external callers)."""
+        num_scenes, _, n_channels, h, w = code.size()
+        if self.code_dropout is not None:
+            code = self.code_dropout(code.reshape(num_scenes * 3, n_channels, h, w)).reshape(num_scenes, 3, n_channels, h, w)
+        if isinstance(xyzs, torch.Tensor):
+            assert xyzs.dim() == 3
+            num_points = xyzs.size(-2)
+            point_code = F.grid_sample(code.reshape(num_scenes * 3, -1, h, w), self.xyz_transform(xyzs), mode=self.interp_mode,
+                                       padding_mode='border', align_corners=False).reshape(num_scenes, 3, -1, num_points)
+            point_code = point_code.permute(0, 3, 2, 1).reshape(num_scenes * num_points, -1)
+            num_points = [num_points] * num_scenes
+        else:
+            num_points, point_code = [], []
+            for code_single, xyzs_single in zip(code, xyzs):
+                n = xyzs_single.size(-2)
+                pc = F.grid_sample(code_single, self.xyz_transform(xyzs_single), mode=self.interp_mode, padding_mode='border',
+                                   align_corners=False).squeeze(-2)
+                point_code.append(pc.permute(2, 1, 0).reshape(n, -1))
+                num_points.append(n)
+            point_code = torch.cat(point_code, dim=0) if len(point_code) > 1 else point_code[0]
+        base_x = self.base_net(point_code)
+        base_x_act = self.base_activation(base_x)
+        sigmas = self.density_net(base_x_act).squeeze(-1)
+        if density_only:
+            return sigmas, None, num_points
+        if self.use_dir_enc:
+            dirs = torch.cat(dirs, dim=0) if num_scenes > 1 else dirs[0]
+            sh_enc = self.dir_encoder(dirs)
+            if self.dir_net is not None:
+                color_in = self.base_activation(base_x + self.dir_net(sh_enc))
+            else:
+                color_in = torch.cat([base_x_act, sh_enc], dim=-1)
+        else:
+            color_in = base_x_act
+        rgbs = self.color_net(color_in)
+        if self.sigmoid_saturation > 0:
+            rgbs = rgbs * (1 + self.sigmoid_saturation * 2) - self.sigmoid_saturation
+        return sigmas, rgbs, num_points
+
+    def point_density_decode(self, xyzs, code, **kwargs):
+        sigmas, _, num_points = self.point_decode(xyzs, None, code, density_only=True, **kwargs)
+        return sigmas, num_points
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma=0, perturb=False, T_thresh=1e-4, return_loss=False):
+        """base_volume_renderer.py:41-133."""
+        num_scenes = len(rays_o)
+        assert num_scenes > 0
+        if self.training:
+            results = self._forward_train(rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh)
+        else:
+            results = self._forward_eval_fused(rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh)
+        if return_loss:
+            results.update(decoder_reg_loss=self.loss())
+        return results
+
+    def _forward_eval_fused(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh):
+        if perturb:
+            raise NotImplementedError('perturb=True in eval mode is not used by the reference (base_nerf.py:518) and not built')
+        if not isinstance(rays_o, torch.Tensor):
+            sizes = {r.size(0) for r in rays_o}
+            if len(sizes) != 1:
+                raise NotImplementedError('fused renderer needs the same number of rays per scene')
+            rays_o, rays_d = torch.stack(list(rays_o)), torch.stack(list(rays_d))
+        num_scenes = rays_o.size(0)
+        if not isinstance(grid_size, int):
+            assert len(set(grid_size)) == 1
+            grid_size = grid_size[0]
+        if isinstance(dt_gamma, (int, float)):
+            dtg = None if dt_gamma == 0 else torch.full((num_scenes,), float(dt_gamma), device=rays_o.device)
+        else:
+            dtg = torch.as_tensor(dt_gamma, dtype=torch.float32, device=rays_o.device).reshape(num_scenes)
+        variant = self.fused_variant()
+        planes = R.pack_planes(code, variant)
+        out = R.render_fwd(variant, planes, tuple(code.shape[-2:]), density_bitfield.reshape(num_scenes, -1), self.packed_blob(),
+                           rays_o=rays_o.reshape(num_scenes, -1, 3), rays_d=rays_d.reshape(num_scenes, -1, 3), grid_size=grid_size,
+                           bound=float(self.bound), min_near=float(self.min_near), max_steps=int(self.max_steps), T_thresh=T_thresh,
+                           dt_gamma=dtg, want_blend=False, want_counts=False)
+        # eval mode returns per-scene lists (base_volume_renderer.py:90-123)
+        return dict(weights_sum=list(out['weights_sum']), depth=list(out['depth']), image=list(out['image']))
+
+    def _forward_train(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh):
+        num_scenes = len(rays_o)
+        if isinstance(grid_size, int):
+            grid_size = [grid_size] * num_scenes
+        if isinstance(dt_gamma, (int, float)):
+            dt_gamma = [float(dt_gamma)] * num_scenes
+        nears, fars = batch_near_far_from_aabb(rays_o, rays_d, self.aabb, self.min_near)
+        xyzs, dirs, deltas, rays = [], [], [], []
+        for ro, rd, bf, ne, fa, gs, dtg in zip(rays_o, rays_d, density_bitfield, nears, fars, grid_size, dt_gamma):
+            x, d, de, r = march_rays_train(ro, rd, self.bound, bf, 1, gs, ne, fa, perturb=perturb, align=128, force_all_rays=True,
+                                           dt_gamma=float(dtg), max_steps=self.max_steps)
+            xyzs.append(x); dirs.append(d); deltas.append(de); rays.append(r)
+        sigmas, rgbs, num_points = self.point_decode(xyzs, dirs, code)
+        weights_sum, depth, image = batch_composite_rays_train(sigmas, rgbs, deltas, rays, num_points, T_thresh)
+        return dict(weights_sum=weights_sum, depth=depth, image=image)

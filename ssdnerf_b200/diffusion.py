@@ -1,0 +1,222 @@
+"""`GaussianDiffusion` -- DDIM sampling over triplane latents, driven from one CUDA stream.
+
+Plugin surface of lib/models/diffusions/gaussian_diffusion.py:14-464 (constructor kwargs, `forward`, `ddim_sample`,
+`sample_from_noise`, `pred_x_0`, schedule attributes, `test_cfg` read at call time).  The sampler differs in HOW it
+runs: the reference re-uploads a 1000-entry table and syncs device->host several times per step
+(gaussian_diffusion.py:190-191,275-279,302-304); here the timestep list and all coefficients are computed once on the
+host (float64, like the reference's NumPy tables), the per-step time-embedding projections are precomputed for every
+step, and ONE captured CUDA graph (UNet forward + fused V->x0->eps->x_prev update, device-side step counter) is
+replayed `num_timesteps` times.
+"""
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as N
+from .registry import MODULES, build_module
+
+
+@MODULES.register_module()
+class GaussianDiffusion(nn.Module):
+
+    def __init__(self, denoising, ddpm_loss=None, betas_cfg=dict(type='cosine'), num_timesteps=1000, num_classes=0,
+                 sample_method='ddim', timestep_sampler=None, denoising_var_mode='FIXED_LARGE', denoising_mean_mode='V',
+                 train_cfg=None, test_cfg=None):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_timesteps = num_timesteps
+        self.sample_method = sample_method
+        self._denoising_cfg = deepcopy(denoising)
+        self.denoising = denoising if isinstance(denoising, nn.Module) else build_module(
+            denoising, default_args=dict(num_classes=num_classes, num_timesteps=num_timesteps))
+        self.denoising_var_mode = denoising_var_mode
+        self.denoising_mean_mode = denoising_mean_mode
+        self.betas_cfg = deepcopy(betas_cfg)
+        self.train_cfg = deepcopy(train_cfg) if train_cfg is not None else dict()
+        self.test_cfg = deepcopy(test_cfg) if test_cfg is not None else dict()
+        # training-only collaborators of the reference (loss, timestep sampler) are configuration we keep but do not build
+        self._ddpm_loss_cfg, self._timestep_sampler_cfg = deepcopy(ddpm_loss), deepcopy(timestep_sampler)
+        self.prepare_diffusion_vars()
+        self._graphs = {}
+        self._graph_kernel_nodes = 0
+
+    # ------------------------------------------------------------------ schedules (gaussian_diffusion.py:64-154)
+    @staticmethod
+    def linear_beta_schedule(diffusion_timesteps, beta_0=1e-4, beta_T=2e-2):
+        scale = 1000 / diffusion_timesteps
+        return np.linspace(scale * beta_0, scale * beta_T, diffusion_timesteps, dtype=np.float64)
+
+    @staticmethod
+    def cosine_beta_schedule(diffusion_timesteps, max_beta=0.999, s=0.008):
+        def f(t, T, s):
+            return np.cos((t / T + s) / (1 + s) * np.pi / 2) ** 2
+        betas = []
+        for t in range(diffusion_timesteps):
+            betas.append(min(1 - f(t + 1, diffusion_timesteps, s) / f(t, diffusion_timesteps, s), max_beta))
+        return np.array(betas)
+
+    def get_betas(self):
+        cfg = dict(self.betas_cfg)
+        self.betas_schedule = cfg.pop('type')
+        if self.betas_schedule == 'linear':
+            return self.linear_beta_schedule(self.num_timesteps, **cfg)
+        if self.betas_schedule == 'cosine':
+            return self.cosine_beta_schedule(self.num_timesteps, **cfg)
+        if self.betas_schedule == 'scaled_linear':
+            return np.linspace(cfg.get('beta_start', 0.0001) ** 0.5, cfg.get('beta_end', 0.02) ** 0.5, self.num_timesteps,
+                               dtype=np.float64) ** 2
+        raise AttributeError(f'Unknown method name {self.betas_schedule} for beta schedule.')
+
+    def prepare_diffusion_vars(self):
+        self.betas = self.get_betas()
+        self.alphas = 1.0 - self.betas
+        self.alphas_bar = np.cumprod(self.alphas, axis=0)
+        self.alphas_bar_prev = np.append(1.0, self.alphas_bar[:-1])
+        self.alphas_bar_next = np.append(self.alphas_bar[1:], 0.0)
+        self.sqrt_alphas_bar = np.sqrt(self.alphas_bar)
+        self.sqrt_one_minus_alphas_bar = np.sqrt(1.0 - self.alphas_bar)
+        self.log_one_minus_alphas_bar = np.log(1.0 - self.alphas_bar)
+        self.sqrt_recip_alplas_bar = np.sqrt(1.0 / self.alphas_bar)
+        self.sqrt_recipm1_alphas_bar = np.sqrt(1.0 / self.alphas_bar - 1)
+        self.tilde_betas_t = self.betas * (1 - self.alphas_bar_prev) / (1 - self.alphas_bar)
+        self.log_tilde_betas_t_clipped = np.log(np.append(self.tilde_betas_t[1], self.tilde_betas_t[1:]))
+        self.tilde_mu_t_coef1 = np.sqrt(self.alphas_bar_prev) / (1 - self.alphas_bar) * self.betas
+        self.tilde_mu_t_coef2 = np.sqrt(self.alphas) * (1 - self.alphas_bar_prev) / (1 - self.alphas_bar)
+
+    # ------------------------------------------------------------------ single-step API
+    @torch.no_grad()
+    def pred_x_0(self, x_t, t, grad_guide_fn=None, concat_cond=None, cfg=dict(), update_denoising_output=False):
+        """gaussian_diffusion.py:180-240 without guidance."""
+        if grad_guide_fn is not None:
+            raise NotImplementedError('guided sampling (grad_guide_fn) needs the renderer backward; planned next (SURVEY.md §8 f1)')
+        clip_denoised = cfg.get('clip_denoised', True)
+        clip_range = cfg.get('clip_range', [-1, 1])
+        num_batches = x_t.size(0)
+        if t.dim() == 0 or len(t) != num_batches:
+            t = t.expand(num_batches)
+        sa = x_t.new_tensor(self.sqrt_alphas_bar)[t].reshape(-1, 1, 1, 1)
+        s1 = x_t.new_tensor(self.sqrt_one_minus_alphas_bar)[t].reshape(-1, 1, 1, 1)
+        out = self.denoising(x_t, t, concat_cond=concat_cond)
+        mode = self.denoising_mean_mode.upper()
+        if mode == 'EPS':
+            x_0 = (x_t - s1 * out) / sa
+        elif mode == 'START_X':
+            x_0 = out
+        elif mode == 'V':
+            x_0 = sa * x_t - s1 * out
+        else:
+            raise AttributeError(f'Unknown denoising mean output type [{self.denoising_mean_mode}].')
+        if clip_denoised:
+            x_0 = x_0.clamp(*clip_range)
+        return x_0, out
+
+    def ddim_timesteps(self, num_timesteps):
+        """gaussian_diffusion.py:302-304, kept on the HOST (the reference moves them to the GPU and syncs per step)"""
+        return torch.arange(start=self.num_timesteps - 1, end=-1, step=-(self.num_timesteps / num_timesteps)).long()
+
+    def ddim_coefficients(self, timesteps, eta=0.0):
+        """float64 host tables -> fp32 rows {sqrt(ab_t), sqrt(1-ab_t), sqrt(ab_prev), sqrt(1-ab_prev-eta^2 beta~_t)} (:275-281)"""
+        rows = []
+        ts = [int(t) for t in timesteps]
+        for i, t in enumerate(ts):
+            t_prev = ts[i + 1] if i + 1 < len(ts) else -1
+            ab_prev = self.alphas_bar[t_prev] if t_prev >= 0 else self.alphas_bar_prev[0]
+            rows.append([self.sqrt_alphas_bar[t], self.sqrt_one_minus_alphas_bar[t], np.sqrt(ab_prev),
+                         np.sqrt(1 - ab_prev - self.tilde_betas_t[t] * eta ** 2)])
+        return torch.tensor(np.asarray(rows, np.float64), dtype=torch.float32)
+
+    # ------------------------------------------------------------------ the loop
+    @torch.no_grad()
+    def ddim_sample(self, noise, show_pbar=False, concat_cond=None, save_intermediates=False, use_graph=True, **kwargs):
+        """gaussian_diffusion.py:295-331 (V-parameterisation, eta = 0, no guidance / langevin / concat_cond)."""
+        if kwargs.get('grad_guide_fn') is not None or self.test_cfg.get('langevin_steps', 0) > 0:
+            raise NotImplementedError('guided / langevin sampling needs the renderer backward; planned next (SURVEY.md §8 f1)')
+        if concat_cond is not None or save_intermediates:
+            raise NotImplementedError('concat_cond / save_intermediates are not part of the accelerated path yet')
+        if self.denoising_mean_mode.upper() != 'V':
+            raise NotImplementedError('the fused DDIM update implements the V-parameterisation every reference config uses')
+        cfg = self.test_cfg
+        eta = cfg.get('eta', 0)
+        if eta != 0:
+            raise NotImplementedError('eta > 0 (stochastic DDIM) is not part of the accelerated path')
+        N.require_cuda(noise)
+        num_steps = cfg.get('num_timesteps', self.num_timesteps)
+        clip = bool(cfg.get('clip_denoised', True))
+        clip_range = tuple(float(c) for c in cfg.get('clip_range', [-1, 1]))
+        dev = noise.device
+        B, C, H, W = noise.shape
+        unet = self.denoising
+        eng = unet.engine(B, dev)
+        key = (id(eng), B, C, H, W, num_steps, clip, clip_range, bool(use_graph))
+        st = self._graphs.get('state')
+        if st is None or st['key'] != key:
+            ts = self.ddim_timesteps(num_steps)
+            st = dict(key=key, S=len(ts), graph=None,
+                      # host-side precompute (no x dependence): coefficient rows + every step's scale/shift projections
+                      coef=self.ddim_coefficients(ts, eta).to(dev),
+                      ss_table=eng.scale_shift_rows(unet.embedding(ts.to(dev))).contiguous(),          # [S, ss_total]
+                      x_t=torch.empty(B, C, H, W, dtype=torch.float32, device=dev),
+                      step_ptr=torch.zeros(1, dtype=torch.int32, device=dev))
+            self._graphs['state'] = st
+        x_t, step_ptr, coef, ss_table, S = st['x_t'], st['step_ptr'], st['coef'], st['ss_table'], st['S']
+        L = N.lib()
+
+        def one_step():
+            s = N.stream_ptr()
+            N.check(L.ssdnerf_select_row(N.ptr(ss_table), N.c_u32(eng.ss_total), N.ptr(step_ptr), N.ptr(eng.ss_cur), N.c_u32(B), s))
+            v = eng.forward_nhwc()
+            N.check(L.ssdnerf_ddim_update(N.ptr(x_t), N.ptr(v), N.c_u32(B), N.c_u32(C), N.c_u32(H), N.c_u32(W), N.c_u32(v.shape[-1]),
+                                          N.ptr(coef), N.ptr(step_ptr), N.c_int(int(clip)), N.c_f32(clip_range[0]), N.c_f32(clip_range[1]),
+                                          None, N.ptr(eng.x_in), N.c_u32(eng.CPAD_IN), s))
+            N.check(L.ssdnerf_step_counter(N.ptr(step_ptr), N.c_int(1), N.c_int(0), s))
+
+        def reset():
+            x_t.copy_(noise.detach().float())
+            step_ptr.zero_()
+            eng.load_input_nchw(x_t)
+
+        if not use_graph:
+            reset()
+            for _ in range(S):
+                one_step()
+            return x_t.clone()
+        if st['graph'] is None:
+            # warm up once on a side stream (lazy allocations / function attributes), then capture ONE step
+            L.ssdnerf_launch_count.restype = __import__('ctypes').c_ulonglong
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                reset()
+                one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            c0 = L.ssdnerf_launch_count()
+            with torch.cuda.graph(graph):
+                one_step()
+            self._graph_kernel_nodes = int(L.ssdnerf_launch_count() - c0)
+            st['graph'] = graph
+        # the S-step loop = S replays of the captured step on the current stream (device-side step counter)
+        reset()
+        for _ in range(S):
+            st['graph'].replay()
+        return x_t.clone()
+
+    def sample_from_noise(self, noise, **kwargs):
+        fn = getattr(self, f'{self.sample_method.lower()}_sample', None)
+        if fn is None:
+            raise AttributeError(f'Cannot find sample method [{self.sample_method.lower()}_sample] correspond to [{self.sample_method}].')
+        return fn(noise=noise, **kwargs)
+
+    def forward_test(self, data, **kwargs):
+        assert data.dim() == 4
+        return self.sample_from_noise(data, **kwargs)
+
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError('diffusion training is outside the accelerated hot paths (SURVEY.md §8 f2)')
+
+    def forward(self, data, return_loss=False, **kwargs):
+        if return_loss:
+            return self.forward_train(data, **kwargs)
+        return self.forward_test(data, **kwargs)

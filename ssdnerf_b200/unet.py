@@ -1,0 +1,382 @@
+"""`DenoisingUnetMod` -- the reference's 2-D UNet over triplane latents, executed by hand-written sm_100a kernels.
+
+Plugin surface kept from the reference (lib/models/architecture/ddpm/denoising.py:12-216, modules.py:12-129):
+constructor kwargs, `forward(x_t, t, label=None, concat_cond=None)` and the state-dict key layout (SURVEY.md
+Appendix D) so released checkpoints load unchanged.  The nn.Module tree below only HOLDS parameters; compute goes
+through `UNetEngine`, which packs the weights to fp16 once and issues the C-ABI kernels of include/ssdnerf_b200.h §4:
+implicit-GEMM 3x3 / 1x1 convolutions and attention GEMMs on tcgen05 tensor cores, GroupNorm(+scale/shift)+SiLU,
+softmax and layout glue as fused memory-bound kernels.  Forward semantics of the blocks the reference inherits from
+mmgen 0.7.2 are restated per SURVEY.md Appendix B.  Inference only (no autograd through the engine).
+"""
+import math
+from copy import deepcopy
+
+import torch
+import torch.nn as nn
+
+from . import _lib as N
+from . import unet_ops as U
+from .registry import MODULES
+
+
+def _gn(c):
+    return nn.GroupNorm(32, c, eps=1e-5)
+
+
+class _ResBlockParams(nn.Module):
+    """parameter container with the key layout of DenoisingResBlockMod (modules.py:51-110)"""
+
+    def __init__(self, cin, cout, emb_ch, dropout=0.0):
+        super().__init__()
+        self.conv_1 = nn.Sequential(_gn(cin), nn.SiLU(), nn.Conv2d(cin, cout, 3, padding=1))
+        self.norm_with_embedding = nn.Module()
+        self.norm_with_embedding.norm = _gn(cout)
+        self.norm_with_embedding.embedding_layer = nn.Sequential(nn.SiLU(), nn.Linear(emb_ch, 2 * cout))
+        conv_2 = [nn.SiLU(), nn.Dropout(dropout), nn.Conv2d(cout, cout, 3, padding=1)] if dropout > 0 \
+            else [nn.SiLU(), nn.Conv2d(cout, cout, 3, padding=1)]
+        self.conv_2 = nn.Sequential(*conv_2)
+        if cin != cout:
+            self.shortcut = nn.Conv2d(cin, cout, 1)
+        self.cin, self.cout = cin, cout
+        nn.init.zeros_(self.conv_2[-1].weight)      # mmgen init_weights: last conv of every ResBlock is zero
+        nn.init.zeros_(self.conv_2[-1].bias)
+
+
+class _AttnParams(nn.Module):
+    """MultiHeadAttentionMod (modules.py:12-26)"""
+
+    def __init__(self, c, num_heads):
+        super().__init__()
+        self.norm = _gn(c)
+        self.qkv = nn.Conv1d(c, 3 * c, 1)
+        self.proj = nn.Conv1d(c, c, 1)
+        self.c, self.num_heads = c, num_heads
+        nn.init.zeros_(self.proj.weight)
+        nn.init.zeros_(self.proj.bias)
+
+
+class _DownParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.downsample = nn.Conv2d(c, c, 3, 2, 1)
+        self.c = c
+
+
+class _UpParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, 1, 1)
+        self.c = c
+
+
+class _TimeEmbedding(nn.Module):
+    """mmgen TimeEmbedding(embedding_mode='sin'): sinusoidal (cos | sin) -> Linear -> SiLU -> Linear"""
+
+    def __init__(self, base, emb_ch):
+        super().__init__()
+        self.blocks = nn.Sequential(nn.Linear(base, emb_ch), nn.SiLU(), nn.Linear(emb_ch, emb_ch))
+        self.base = base
+
+    def forward(self, t):
+        half = self.base // 2
+        freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+        args = t[:, None].float() * freqs[None]
+        return self.blocks(torch.cat([torch.cos(args), torch.sin(args)], dim=-1))
+
+
+@MODULES.register_module()
+class DenoisingUnetMod(nn.Module):
+    """Same constructor signature as lib/models/architecture/ddpm/denoising.py:14-43 (groups must be 1)."""
+
+    def __init__(self, image_size, in_channels=3, concat_cond_channels=0, base_channels=128, resblocks_per_downsample=3,
+                 num_timesteps=1000, use_rescale_timesteps=True, dropout=0, embedding_channels=-1, num_classes=0,
+                 channels_cfg=None, groups=1, norm_cfg=dict(type='GN', num_groups=32), act_cfg=dict(type='SiLU', inplace=False),
+                 shortcut_kernel_size=1, use_scale_shift_norm=False, num_heads=4, time_embedding_mode='sin',
+                 time_embedding_cfg=None, resblock_cfg=dict(type='DenoisingResBlockMod'),
+                 attention_cfg=dict(type='MultiHeadAttentionMod'), downsample_conv=True, upsample_conv=True,
+                 downsample_cfg=dict(type='DenoisingDownsampleMod'), upsample_cfg=dict(type='DenoisingUpsampleMod'),
+                 attention_res=[16, 8], pretrained=None):
+        super().__init__()
+        unsupported = []
+        if groups != 1: unsupported.append('groups != 1')
+        if num_classes != 0: unsupported.append('class conditioning')
+        if not use_scale_shift_norm: unsupported.append('use_scale_shift_norm=False')
+        if shortcut_kernel_size != 1: unsupported.append('shortcut_kernel_size != 1')
+        if not (downsample_conv and upsample_conv): unsupported.append('pool / bare-interpolate resampling')
+        if norm_cfg.get('type') != 'GN' or norm_cfg.get('num_groups', 32) != 32: unsupported.append('norm other than GN32')
+        if act_cfg.get('type') != 'SiLU': unsupported.append('activation other than SiLU')
+        if time_embedding_mode != 'sin': unsupported.append('time_embedding_mode != sin')
+        if unsupported:
+            raise NotImplementedError('ssdnerf_b200.DenoisingUnetMod covers the configurations the reference ships; unsupported: '
+                                      + ', '.join(unsupported))
+        if not isinstance(channels_cfg, (list, tuple)):
+            raise ValueError(f'Only support list for `channels_cfg`, receive {type(channels_cfg)}')
+        self.num_classes, self.num_timesteps, self.use_rescale_timesteps = num_classes, num_timesteps, use_rescale_timesteps
+        self.out_channels = in_channels
+        self.in_channels = in_channels
+        self.concat_cond_channels = concat_cond_channels
+        if isinstance(image_size, int):
+            image_size = [image_size, image_size]
+        assert len(image_size) == 2, 'The length of `image_size` should be 2.'
+        self.image_size = list(image_size)
+        self.channel_factor_list = list(channels_cfg)
+        self.num_heads = num_heads
+        self.base_channels = base_channels
+        emb_ch = base_channels * 4 if embedding_channels == -1 else embedding_channels
+        self.embedding_channels = emb_ch
+        self.time_embedding = _TimeEmbedding(base_channels, emb_ch)
+
+        attention_scale = [min(image_size) // int(res) for res in attention_res]
+        scale = 1
+        self.in_blocks = nn.ModuleList([nn.Sequential(nn.Conv2d(in_channels + concat_cond_channels, base_channels, 3, 1, padding=1))])
+        self.in_channels_list = [base_channels]
+        cin = base_channels
+        for level, factor in enumerate(self.channel_factor_list):
+            cin = base_channels if level == 0 else base_channels * self.channel_factor_list[level - 1]
+            cout = base_channels * factor
+            for _ in range(resblocks_per_downsample):
+                layers = [_ResBlockParams(cin, cout, emb_ch, dropout)]
+                cin = cout
+                if scale in attention_scale:
+                    layers.append(_AttnParams(cin, num_heads))
+                self.in_channels_list.append(cin)
+                self.in_blocks.append(nn.Sequential(*layers))
+            if level != len(self.channel_factor_list) - 1:
+                self.in_blocks.append(nn.Sequential(_DownParams(cin)))
+                self.in_channels_list.append(cin)
+                scale *= 2
+        self.mid_blocks = nn.Sequential(_ResBlockParams(cin, cin, emb_ch, dropout), _AttnParams(cin, num_heads),
+                                        _ResBlockParams(cin, cin, emb_ch, dropout))
+        in_list = deepcopy(self.in_channels_list)
+        self.out_blocks = nn.ModuleList()
+        for level, factor in enumerate(self.channel_factor_list[::-1]):
+            for idx in range(resblocks_per_downsample + 1):
+                layers = [_ResBlockParams(cin + in_list.pop(), base_channels * factor, emb_ch, dropout)]
+                cin = base_channels * factor
+                if scale in attention_scale:
+                    layers.append(_AttnParams(cin, num_heads))
+                if level != len(self.channel_factor_list) - 1 and idx == resblocks_per_downsample:
+                    layers.append(_UpParams(cin))
+                    scale //= 2
+                self.out_blocks.append(nn.Sequential(*layers))
+        self.out = nn.Module()
+        self.out.gn = _gn(cin)
+        self.out.conv = nn.Conv2d(cin, in_channels, 3, padding=1)
+        self._engine = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ reference-facing API
+    def engine(self, batch, device=None):
+        """(re)build the native engine for a batch size; weights are re-packed when parameters changed"""
+        device = device or next(self.parameters()).device
+        key = (batch, str(device), tuple(p._version for p in self.parameters()))
+        if self._engine is None or self._engine_key != key:
+            self._engine = UNetEngine(self, batch, device)
+            self._engine_key = key
+        return self._engine
+
+    def embedding(self, t):
+        if self.use_rescale_timesteps:
+            t = t.float() * (1000.0 / self.num_timesteps)
+        return self.time_embedding(t)
+
+    @torch.no_grad()
+    def forward(self, x_t, t, label=None, concat_cond=None, return_noise=False):
+        """denoising.py:191-216. x_t [B,C,H,W] float; t [B] long. Returns fp32 [B,C,H,W]."""
+        if label is not None:
+            raise NotImplementedError('class-conditional embedding is not built (num_classes == 0 in every reference config)')
+        N.require_cuda(x_t)
+        h = x_t
+        if self.concat_cond_channels > 0:
+            h = torch.cat([h, concat_cond], dim=1)
+        B = h.shape[0]
+        eng = self.engine(B, h.device)
+        if t.dim() == 0 or t.numel() != B:
+            t = t.expand(B)
+        eng.set_embedding(self.embedding(t.to(h.device)))
+        v = eng.forward_nchw(h.float().contiguous())
+        return v.permute(0, 3, 1, 2)[:, :self.out_channels].contiguous()
+
+
+class UNetEngine:
+    """Packed fp16 weights + activation arena + launch sequence for one batch size."""
+
+    CPAD_IN = 64
+
+    def __init__(self, m: DenoisingUnetMod, batch, device):
+        self.m, self.B, self.dev = m, batch, torch.device(device)
+        self.H, self.W = m.image_size
+        self.bufs = {}
+        self.cin_total = m.in_channels + m.concat_cond_channels
+        assert self.cin_total <= self.CPAD_IN
+        dev = self.dev
+        f32 = lambda p: p.detach().float().contiguous().to(dev)
+        # ---- op list + packed weights
+        self.ops = []            # (kind, params dict)
+        self.res_blocks = []     # for the scale/shift table
+        self.n_norm = 0
+
+        def res(p):
+            d = dict(cin=p.cin, cout=p.cout, g1=f32(p.conv_1[0].weight), b1=f32(p.conv_1[0].bias),
+                     w1=U.pack_conv_weight(p.conv_1[2].weight).to(dev), c1b=f32(p.conv_1[2].bias),
+                     g2=f32(p.norm_with_embedding.norm.weight), b2=f32(p.norm_with_embedding.norm.bias),
+                     w2=U.pack_conv_weight(p.conv_2[-1].weight).to(dev), c2b=f32(p.conv_2[-1].bias),
+                     emb_w=f32(p.norm_with_embedding.embedding_layer[1].weight), emb_b=f32(p.norm_with_embedding.embedding_layer[1].bias),
+                     n1=self._norm_slot(), n2=self._norm_slot(), idx=len(self.res_blocks))
+            if hasattr(p, 'shortcut'):
+                d['ws'] = U.pack_linear_weight(p.shortcut.weight).to(dev)
+                d['wsb'] = f32(p.shortcut.bias)
+            self.res_blocks.append(d)
+            return ('res', d)
+
+        def attn(p):
+            return ('attn', dict(c=p.c, heads=p.num_heads, g=f32(p.norm.weight), b=f32(p.norm.bias),
+                                 wqkv=U.pack_linear_weight(p.qkv.weight).to(dev), bqkv=f32(p.qkv.bias),
+                                 wproj=U.pack_linear_weight(p.proj.weight).to(dev), bproj=f32(p.proj.bias), n=self._norm_slot()))
+
+        def layer(p):
+            if isinstance(p, _ResBlockParams): return res(p)
+            if isinstance(p, _AttnParams): return attn(p)
+            if isinstance(p, _DownParams):
+                w = p.downsample.weight.detach().permute(0, 2, 3, 1).reshape(p.c, 9 * p.c)      # K index = tap*C + c
+                return ('down', dict(c=p.c, w=U.pack_linear_weight(w).to(dev), b=f32(p.downsample.bias)))
+            if isinstance(p, _UpParams):
+                return ('up', dict(c=p.c, w=U.pack_conv_weight(p.conv.weight).to(dev), b=f32(p.conv.bias)))
+            raise TypeError(type(p))
+
+        conv_in = m.in_blocks[0][0]
+        self.conv_in = dict(w=U.pack_conv_weight(conv_in.weight, cin_pad=self.CPAD_IN).to(dev), b=f32(conv_in.bias), cout=conv_in.out_channels)
+        self.in_seq = [[layer(p) for p in blk] for blk in list(m.in_blocks)[1:]]
+        self.mid_seq = [layer(p) for p in m.mid_blocks]
+        self.out_seq = [[layer(p) for p in blk] for blk in m.out_blocks]
+        self.out_norm = dict(g=f32(m.out.gn.weight), b=f32(m.out.gn.bias), n=self._norm_slot(), c=m.out.gn.num_channels)
+        self.out_conv = dict(w=U.pack_conv_weight(m.out.conv.weight).to(dev), b=f32(m.out.conv.bias), cout=m.out.conv.out_channels)
+        # ---- GroupNorm statistics arena (zeroed once per forward) and scale/shift row (one per sample)
+        self.stats = torch.zeros(self.n_norm, batch, 32, 2, dtype=torch.float32, device=dev)
+        self.ss_offsets, off = [], 0
+        for d in self.res_blocks:
+            self.ss_offsets.append(off)
+            off += 2 * d['cout']
+        self.ss_total = off
+        self.ss_cur = torch.zeros(batch, self.ss_total, dtype=torch.float32, device=dev)
+        self.x_in = torch.zeros(batch, self.H, self.W, self.CPAD_IN, dtype=torch.float16, device=dev)
+        self.v_out = torch.zeros(batch, self.H, self.W, self.out_conv['cout'], dtype=torch.float32, device=dev)
+
+    def _norm_slot(self):
+        self.n_norm += 1
+        return self.n_norm - 1
+
+    def _buf(self, key, shape, dtype=torch.float16):
+        t = self.bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(*shape, dtype=dtype, device=self.dev)
+            self.bufs[key] = t
+        return t
+
+    # ------------------------------------------------------------------ embeddings
+    def scale_shift_rows(self, emb):
+        """emb [R, emb_ch] -> [R, ss_total]: every ResBlock's Linear(SiLU(emb)) (NormWithEmbedding.embedding_layer)."""
+        e = torch.nn.functional.silu(emb.float())
+        return torch.cat([torch.nn.functional.linear(e, d['emb_w'], d['emb_b']) for d in self.res_blocks], dim=1)
+
+    def set_embedding(self, emb):
+        """per-sample time embedding [B, emb_ch] for the next forward"""
+        self.ss_cur.copy_(self.scale_shift_rows(emb))
+
+    # ------------------------------------------------------------------ kernels
+    def _gn(self, slot, x1, x2, gamma, beta, out, silu, ss_off=None):
+        B, H, W, C1 = x1.shape
+        C2 = x2.shape[-1] if x2 is not None else 0
+        st = self.stats[slot]
+        L, s = N.lib(), N.stream_ptr()
+        N.check(L.ssdnerf_gn_stats(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st), s))
+        ss = None
+        if ss_off is not None:
+            ss = N.c_void_p(self.ss_cur.data_ptr() + 4 * ss_off)
+        N.check(L.ssdnerf_gn_apply(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st),
+                                   N.ptr(gamma), N.ptr(beta), ss, N.c_longlong(self.ss_total), N.c_f32(1e-5), N.c_int(int(silu)),
+                                   N.ptr(out), s))
+        return out
+
+    def _res(self, d, x, skip, tag):
+        B, H, W, _ = x.shape
+        cin, cout = d['cin'], d['cout']
+        a = self._gn(d['n1'], x, skip, d['g1'], d['b1'], self._buf(('a', H, cin), (B, H, W, cin)), True)
+        h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', H, cout), (B, H, W, cout)))
+        a2 = self._gn(d['n2'], h1, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
+        if 'ws' in d:
+            sc = U.conv3x3_f16(x, d['ws'].unsqueeze(0), cout, bias=d['wsb'], x2=skip, taps=1, out=self._buf(('sc', H, cout), (B, H, W, cout)))
+        else:
+            sc = x
+        return U.conv3x3_f16(a2, d['w2'], cout, bias=d['c2b'], residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)))
+
+    def _attn(self, d, x, tag):
+        B, H, W, c = x.shape
+        T, heads = H * W, d['heads']
+        ch = c // heads
+        L, s = N.lib(), N.stream_ptr()
+        xn = self._gn(d['n'], x, None, d['g'], d['b'], self._buf(('xn', T, c), (B, H, W, c)), False)
+        qkv = U.linear_f16(xn.view(B * T, c), d['wqkv'], bias=d['bqkv'], n=3 * c, out=self._buf(('qkv', T, c), (B * T, 3 * c)))
+        S = U.attn_scores(qkv.view(B, T, 3 * c), heads, scale=1.0 / math.sqrt(ch), out=self._buf(('S', T), (B, heads, T, T), torch.float32))
+        P = self._buf(('P', T), (B, heads, T, T))
+        N.check(L.ssdnerf_softmax_rows(N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(P), s))
+        vt = self._buf(('vt', T, c), (B, heads, ch, T))
+        N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
+        o = U.attn_pv(P, vt, out=self._buf(('o', T, c), (B, T, c)))
+        return U.linear_f16(o.view(B * T, c), d['wproj'], bias=d['bproj'], residual=x.view(B * T, c), n=c,
+                            out=self._buf(('attn_out', tag), (B * T, c))).view(B, H, W, c)
+
+    def _down(self, d, x, tag):
+        B, H, W, c = x.shape
+        col = self._buf(('col', H, c), (B, H // 2, W // 2, 9 * c))
+        N.check(N.lib().ssdnerf_im2col_s2(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(col), N.stream_ptr()))
+        M = B * (H // 2) * (W // 2)
+        return U.linear_f16(col.view(M, 9 * c), d['w'], bias=d['b'], n=c, out=self._buf(('down_out', tag), (M, c))).view(B, H // 2, W // 2, c)
+
+    def _up(self, d, x, tag):
+        B, H, W, c = x.shape
+        up = self._buf(('upx', H, c), (B, 2 * H, 2 * W, c))
+        N.check(N.lib().ssdnerf_upsample2x(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(up), N.stream_ptr()))
+        return U.conv3x3_f16(up, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)))
+
+    def _run(self, layers, h, skip, tag):
+        for li, (kind, d) in enumerate(layers):
+            t = (tag, li)
+            if kind == 'res':
+                h = self._res(d, h, skip, t)
+                skip = None
+            elif kind == 'attn':
+                h = self._attn(d, h, t)
+            elif kind == 'down':
+                h = self._down(d, h, t)
+            elif kind == 'up':
+                h = self._up(d, h, t)
+        return h
+
+    # ------------------------------------------------------------------ forward
+    def forward_nhwc(self):
+        """x_in (self.x_in, fp16 NHWC padded) -> self.v_out (fp32 NHWC); all launches on the current stream, capture-safe."""
+        self.stats.zero_()
+        h = U.conv3x3_f16(self.x_in, self.conv_in['w'], self.conv_in['cout'], bias=self.conv_in['b'],
+                          out=self._buf(('conv_in',), (self.B, self.H, self.W, self.conv_in['cout'])))
+        hs = [h]
+        for i, layers in enumerate(self.in_seq):
+            h = self._run(layers, h, None, ('in', i))
+            hs.append(h)
+        h = self._run(self.mid_seq, h, None, ('mid',))
+        for j, layers in enumerate(self.out_seq):
+            h = self._run(layers, h, hs.pop(), ('out', j))
+        B, H, W, c = h.shape
+        a = self._gn(self.out_norm['n'], h, None, self.out_norm['g'], self.out_norm['b'], self._buf(('a', H, c), (B, H, W, c)), True)
+        U.conv3x3_f16(a, self.out_conv['w'], self.out_conv['cout'], bias=self.out_conv['b'], out=self.v_out)
+        return self.v_out
+
+    def load_input_nchw(self, x):
+        """x fp32 [B,C,H,W] -> self.x_in"""
+        B, C, H, W = x.shape
+        N.check(N.lib().ssdnerf_nchw_to_nhwc_f16(N.ptr(x), N.c_u32(B), N.c_u32(C), N.c_u32(H), N.c_u32(W), N.c_u32(self.CPAD_IN),
+                                                 N.ptr(self.x_in), N.stream_ptr()))
+
+    def forward_nchw(self, x):
+        self.load_input_nchw(x)
+        return self.forward_nhwc()

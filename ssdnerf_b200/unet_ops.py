@@ -142,3 +142,25 @@ def attn_scores(qkv, heads, scale, out=None):
     g.so1, g.so2, g.so3 = T, T * T, heads * T * T
     _launch(g)
     return out
+
+
+def attn_pv(P, vt, out=None):
+    """O[b,t,h*ch + c] = sum_s P[b,h,t,s] * vt[b,h,c,s]   (P fp16 [B,heads,T,T], vt fp16 [B,heads,ch,T]) -> fp16 [B,T,heads*ch]"""
+    B, heads, T, _ = P.shape
+    ch = vt.shape[2]
+    c = heads * ch
+    assert T % 64 == 0
+    if out is None:
+        out = torch.empty(B, T, c, dtype=torch.float16, device=P.device)
+    g = GemmArgs()
+    g.a1, g.k1 = P.data_ptr(), T
+    g.a1_strides = (c_u64 * 3)(T * 2, T * T * 2, heads * T * T * 2)
+    g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = T, heads, B, 128, 1, 1
+    g.taps = 1
+    g.b, g.n, g.n_rows_b, g.bx2, g.bx3, g.b_batched = vt.data_ptr(), ch, ch, heads, B, 1
+    g.b_strides = (c_u64 * 3)(T * 2, ch * T * 2, heads * ch * T * 2)
+    g.bn, g.alpha = 0, 1.0
+    g.out, g.out_f32 = out.data_ptr(), 0
+    g.so1, g.so2, g.so3 = c, ch, T * c
+    _launch(g)
+    return out
