@@ -276,13 +276,26 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------------- reference arm
+def usable_cores():
+    """host cores this process may really use: affinity mask capped by the cgroup CPU quota (a 128-thread pool on an
+    8-core quota is ~100x slower than 8 threads)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_reference_sample(quick=False, unet_evals=4, views=4):
     """Reference arithmetic on the host cores = the oracle port (PyTorch-CPU UNet + C marcher/compositor + PyTorch-CPU decode);
     the reference itself has no CPU path for the renderer. Bounded sample of the bench workload:
     B=1 scene, `unet_evals` UNet evaluations (extrapolated x50/`unet_evals`), `views` 128x128 views."""
     from oracle import render_port as rp
     from oracle import unet_port as up
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     if quick:
         unet_evals, views = 2, 1
