@@ -95,6 +95,9 @@ SSDNERF_API int ssdnerf_sh_encode_backward(const float* grad, const float* input
 /* Decoder variants (template instantiations). */
 #define SSDNERF_DEC_P 0 /* shipped configs: base 3*6->64, density 64->1, dir_net 16->64, color 64->3
                            (configs/paper_cfgs/ssdnerf_cars_uncond.py:40-51) */
+#define SSDNERF_DEC_P_SIMT 2 /* decoder P on the CUDA cores in plain fp32 (csrc/render_fused.cu) */
+#define SSDNERF_DEC_P_TC 3   /* decoder P with the base layer as a split-precision fp16 tcgen05 GEMM (csrc/render_ptc.cu);
+                                SSDNERF_DEC_P selects whichever of the two is currently faster */
 #define SSDNERF_DEC_S 1 /* TriPlaneDecoder class defaults: base 3*32->128, density 128->1, color (128+16)->128->3
                            (lib/models/decoders/triplane_decoder.py:24-39) */
 
@@ -185,6 +188,7 @@ typedef struct ssdnerf_gemm_args {
      *    conv / plain: coordinate 2 = tap; b_batched: coordinates (2, 3) = the tile's (d2, d3) tile indices */
     const void* b; uint64_t b_strides[3]; uint32_t n, n_rows_b, bx2, bx3; uint32_t b_batched;
     uint32_t bn;              /* N tile: 0 = auto, else 64 / 128 / 256 */
+    uint32_t cluster;         /* 0 = auto, 1 = no cluster, 2 = CTA pairs along M with TMA multicast of the B tile */
     float alpha;
     const float* bias_n;      /* [n] fp32 or NULL */
     const void* residual;     /* fp16, addressed like out, or NULL */

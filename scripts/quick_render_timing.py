@@ -9,17 +9,18 @@ from tests.common import spiral_poses
 dev = torch.device('cuda:0')
 variant = sys.argv[1] if len(sys.argv) > 1 else 'P'
 B, V, res = int(os.environ.get('B', 16)), int(os.environ.get('V', 8)), 128
-vid = R.DEC_P if variant == 'P' else R.DEC_S
-C = 6 if variant == 'P' else 32
+vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'S': R.DEC_S}[variant]
+C = 32 if variant == 'S' else 6
 g = torch.Generator().manual_seed(0)
 code = torch.randn(B, 3, C, 128, 128, generator=g).clamp(-2, 2).to(dev)
-params = rp.make_decoder_params(variant, 0)
+params = rp.make_decoder_params(variant[0], 0)
 blob = R.pack_decoder_blob(params, vid, device=dev)
 planes = R.pack_planes(code, vid)
-bf = torch.from_numpy(rp.sphere_bitfield())[None].repeat(B, 1).to(dev)
+import numpy as _np
+bf = torch.from_numpy(rp.sphere_bitfield() if os.environ.get('GRID', 'sphere') == 'sphere' else _np.full(64**3//8, 255, _np.uint8))[None].repeat(B, 1).to(dev)
 poses = torch.from_numpy(spiral_poses(V))[None].repeat(B, 1, 1, 1).to(dev)
 intr = torch.tensor([131.25, 131.25, 64, 64]).expand(B, V, 4).contiguous().to(dev)
-for emu in (1, 0):
+for emu in (1,):
     for _ in range(3):
         out = R.render_fwd(vid, planes, (128, 128), bf, blob, poses=poses, intrinsics=intr, img_hw=(res, res), emulate_schedule=bool(emu))
     torch.cuda.synchronize()

@@ -52,7 +52,9 @@ struct GemmCfg {
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// CL = cluster size along M: the CL CTAs of a cluster work on CL consecutive M tiles of the same N tile; each loads 1/CL of the
+// B (weight) tile and TMA-multicasts it to all of them, so the L2 -> SM operand traffic per CTA drops from A + B to A + B/CL.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
@@ -69,27 +71,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
-    const uint32_t total_tiles = tiles_m * p.tiles_n;
+    const uint32_t sup_m = (tiles_m + CL - 1) / CL;                 // super-tiles (CL M tiles) along M
+    const uint32_t total_tiles = sup_m * p.tiles_n;                   // work items per cluster
     const uint32_t iters = p.taps * (p.kc1 + p.kc2);
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    const uint32_t tile0 = (CL > 1) ? cluster_id_x() : blockIdx.x;
+    const uint32_t tile_step = (CL > 1) ? num_clusters_x() : gridDim.x;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA1); prefetch_tmap(&mapA2); prefetch_tmap(&mapB);
-        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();       // peers' barriers are initialised before any multicast load / remote arrive targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {   // ---------------- TMA producer
             uint32_t stage = 0, phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const uint32_t m_tile = tile % tiles_m, n_tile = tile / tiles_m;
-                const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);
+            for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
+                const uint32_t m_tile = (tile % sup_m) * CL + crank, n_tile = tile / sup_m;     // m_tile may be >= tiles_m in the last
+                const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);   // super-tile: loads zero-fill
                 for (uint32_t tap = 0; tap < p.taps; ++tap) {
                     const int ox = (p.taps == 9) ? (int)(tap % 3) - 1 : 0;
                     const int oy = (p.taps == 9) ? (int)(tap / 3) - 1 : 0;
@@ -100,8 +108,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                         tma_load_4d(sA + stage * kABytes, first ? &mapA1 : &mapA2, &full[stage],
                                     (int)((first ? j : j - p.kc1) * kBK), (int)(t1 * p.b1) + ox, (int)(t2 * p.b2) + oy,
                                     (int)(t3 * p.b3));
-                        tma_load_4d(sB + stage * Cfg::kBBytes, &mapB, &full[stage], (int)(j * kBK), (int)(n_tile * BN),
-                                    p.b_batched ? (int)t2 : (int)tap, p.b_batched ? (int)t3 : 0);
+                        if (CL == 1) {
+                            tma_load_4d(sB + stage * Cfg::kBBytes, &mapB, &full[stage], (int)(j * kBK), (int)(n_tile * BN),
+                                        p.b_batched ? (int)t2 : (int)tap, p.b_batched ? (int)t3 : 0);
+                        } else {   // this CTA's 1/CL slice of the B tile, broadcast to the whole cluster
+                            constexpr int kSlice = BN / CL;
+                            tma_load_4d_mc(sB + stage * Cfg::kBBytes + crank * kSlice * 128, &mapB, &full[stage], (int)(j * kBK),
+                                           (int)(n_tile * BN + crank * kSlice), (int)tap, 0, kMask);
+                        }
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -112,7 +126,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         if (lane == 0) {   // ---------------- MMA issuer
             constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -124,7 +138,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 #pragma unroll
                     for (uint32_t k = 0; k < kBK / 16; ++k)   // advance 16 halves = 32 B = 2 descriptor units along K
                         umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
-                    umma_commit(&empty[stage]);
+                    if (CL == 1) umma_commit(&empty[stage]);
+                    else umma_commit_mc(&empty[stage], kMask);     // frees this stage in every CTA that multicasts into it
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
@@ -137,11 +152,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         const uint32_t row = q * 32 + (uint32_t)lane;
         const uint32_t i1 = row % p.b1, i2 = (row / p.b1) % p.b2, i3 = row / (p.b1 * p.b2);
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const uint32_t m_tile = tile % tiles_m, n_tile = tile / tiles_m;
+        for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
+            const uint32_t m_tile = (tile % sup_m) * CL + crank, n_tile = tile / sup_m;
             const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);
             const uint32_t g1 = t1 * p.b1 + i1, g2 = t2 * p.b2 + i2, g3 = t3 * p.b3 + i3;
-            const bool row_ok = g1 < p.d1 && g2 < p.d2 && g3 < p.d3;
+            const bool row_ok = m_tile < tiles_m && g1 < p.d1 && g2 < p.d2 && g3 < p.d3;
             const long long off = (long long)g1 * p.so1 + (long long)g2 * p.so2 + (long long)g3 * p.so3 + (long long)n_tile * BN;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -206,6 +221,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();       // nobody exits while a peer may still multicast into its shared memory
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
@@ -248,18 +264,29 @@ static int make_map_4d(CUtensorMap* m, const void* base, uint64_t K, uint64_t e1
     return 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const GemmParams& p, int sms,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr = false;
     if (!attr) {
-        SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
         attr = true;
     }
-    const uint32_t total = p.T1 * p.T2 * p.T3 * p.tiles_n;
-    const uint32_t grid = total < (uint32_t)sms ? total : (uint32_t)sms;
-    k_gemm_tc<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(mA1, mA2, mB, p);
+    const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
+    const uint32_t total = ((tiles_m + CL - 1) / CL) * p.tiles_n;          // work items per cluster (CL = 1: per CTA)
+    const uint32_t max_clusters = (uint32_t)sms / CL;
+    const uint32_t clusters = total < max_clusters ? total : max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SSDNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL>, mA1, mA2, mB, p));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -276,7 +303,24 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     if (a->taps != 1 && a->taps != 9) return set_error_msg(SSDNERF_ERR_ARG, "gemm: taps must be 1 or 9");
     if (a->taps == 9 && a->b_batched) return set_error_msg(SSDNERF_ERR_ARG, "gemm: conv taps and batched B are exclusive");
     if (a->n == 0 || a->d1 == 0 || a->d2 == 0 || a->d3 == 0) return 0;
-    const int bn = a->bn ? a->bn : (a->n > 128 ? 256 : (a->n > 64 ? 128 : 64));
+    int dev = 0, sms = 0;
+    SSDNERF_CUDA_OK(cudaGetDevice(&dev));
+    SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int bn = (int)a->bn;
+    if (!bn) {
+        // pick the N tile that minimises (waves x tile cost): wide tiles amortise A loads (N=256 runs the MMA pipe at full rate,
+        // N=128 is shared-memory-bandwidth limited, N=64 more so) but small problems need more tiles to fill 148 SMs
+        const uint32_t tiles_m = div_up(a->d1, a->b1) * div_up(a->d2, a->b2) * div_up(a->d3, a->b3);
+        double best = 1e30;
+        const int cand[3] = {256, 128, 64};
+        const double eff[3] = {1.0, 0.80, 0.50};
+        for (int i = 0; i < 3; ++i) {
+            if (cand[i] > 64 && (uint32_t)cand[i] / 2 >= a->n) continue;          // tile mostly padding
+            const uint32_t tiles = tiles_m * div_up(a->n, (uint32_t)cand[i]);
+            const double t = (double)div_up(tiles, (uint32_t)sms) * cand[i] / eff[i];
+            if (t < best) { best = t; bn = cand[i]; }
+        }
+    }
     if (bn != 64 && bn != 128 && bn != 256) return set_error_msg(SSDNERF_ERR_ARG, "gemm: bn must be 64, 128 or 256");
     if (a->residual && a->out_f32 == 0 && a->residual == a->out) { /* in-place residual add is fine: same thread reads then writes */ }
 
@@ -296,14 +340,15 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     } else {
         mA2 = mA1;
     }
-    // B: {K, N, x2, x3}; box {64, bn, 1, 1}
+    // cluster of 2 along M with multicast of the weight tile: only for non-batched B and problems with >= 2 waves of M tiles
+    const uint32_t tiles_m_all = p.T1 * p.T2 * p.T3;
+    int cl = (!a->b_batched && a->cluster != 1 && bn >= 128 && tiles_m_all * p.tiles_n >= 2u * (uint32_t)sms) ? 2 : 1;
+    if (a->cluster == 2 && !a->b_batched && bn >= 128) cl = 2;
+    // B: {K, N, x2, x3}; box {64, bn / cl, 1, 1}
     if (int e = make_map_4d(&mB, a->b, ktot, a->n_rows_b ? a->n_rows_b : a->n, a->bx2 ? a->bx2 : 1, a->bx3 ? a->bx3 : 1, a->b_strides[0],
-                            a->b_strides[1], a->b_strides[2], (uint32_t)bn, 1, 1)) return e;
+                            a->b_strides[1], a->b_strides[2], (uint32_t)(bn / cl), 1, 1)) return e;
 
-    int dev = 0, sms = 0;
-    SSDNERF_CUDA_OK(cudaGetDevice(&dev));
-    SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (bn == 256) return launch_gemm<256>(mA1, mA2, mB, p, sms, stream);
-    if (bn == 128) return launch_gemm<128>(mA1, mA2, mB, p, sms, stream);
-    return launch_gemm<64>(mA1, mA2, mB, p, sms, stream);
+    if (bn == 256) return cl == 2 ? launch_gemm<256, 2>(mA1, mA2, mB, p, sms, stream) : launch_gemm<256, 1>(mA1, mA2, mB, p, sms, stream);
+    if (bn == 128) return cl == 2 ? launch_gemm<128, 2>(mA1, mA2, mB, p, sms, stream) : launch_gemm<128, 1>(mA1, mA2, mB, p, sms, stream);
+    return launch_gemm<64, 1>(mA1, mA2, mB, p, sms, stream);
 }

@@ -259,14 +259,14 @@ using namespace ssdnerf;
 extern "C" {
 
 size_t ssdnerf_decoder_blob_floats(int variant) {
-    if (variant == SSDNERF_DEC_P) return DecP::BLOB;
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC) return DecP::BLOB;
     if (variant == SSDNERF_DEC_S) return ssdnerf::dec_s_blob_floats();
     return 0;
 }
 
 size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp) {
     const size_t texels = (size_t)B * 3 * Hp * Wp;
-    if (variant == SSDNERF_DEC_P) return texels * 8 * sizeof(float);
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC) return texels * 8 * sizeof(float);
     if (variant == SSDNERF_DEC_S) return texels * 32 * sizeof(__half);
     return 0;
 }
@@ -277,7 +277,7 @@ int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, 
     if (total == 0) return 0;
     if (((uintptr_t)planes & 15u) != 0) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: planes must be 16-byte aligned");
     const uint32_t blocks = (uint32_t)((total + 255) / 256);
-    if (variant == SSDNERF_DEC_P) {
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC) {
         if (C != 6) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: variant P expects 6 channels per plane");
         k_pack_planes<float, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(code, B, C, Hp, Wp, (float*)planes);
     } else if (variant == SSDNERF_DEC_S) {
@@ -346,7 +346,8 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
     SSDNERF_CUDA_OK(cudaGetDevice(&dev));
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
-    if (a->variant == SSDNERF_DEC_P) {
+    if (a->variant == SSDNERF_DEC_P_TC) return ssdnerf::render_ptc_launch(p, a->emulate_schedule, hist, sms, stream);
+    if (a->variant == SSDNERF_DEC_P || a->variant == SSDNERF_DEC_P_SIMT) {
         const size_t smem = sizeof(SmemP);
         static bool attr_set = false;
         if (!attr_set) {

@@ -61,7 +61,20 @@ __global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x1,
         for (int k = 0; k < 8; ++k) { s[k] = 0.0f; q[k] = 0.0f; }
         const __half* src = v < cv1 ? x1 + (size_t)b * HW * C1 + v * 8 : x2 + (size_t)b * HW * C2 + (v - cv1) * 8;
         const uint32_t cs = v < cv1 ? C1 : C2;
-        for (uint32_t p = p0 + lane_p; p < p1; p += pstep) {
+        uint32_t p = p0 + lane_p;
+        for (; p + 3 * pstep < p1; p += 4 * pstep) {   // 4 independent 16-byte loads in flight per thread
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(p + u * pstep) * cs));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                h8_to_f(r[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+            }
+        }
+        for (; p < p1; p += pstep) {
             float f[8];
             h8_to_f(__ldg(reinterpret_cast<const uint4*>(src + (size_t)p * cs)), f);
 #pragma unroll
@@ -81,40 +94,51 @@ __global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x1,
 }
 
 // ---------------------------------------------------------------- GroupNorm apply (+ scale/shift) (+ SiLU)
+// grid (pixel chunks, B), blockDim.x = cv * pr.  Each thread owns one 8-channel vector: mean/rstd/gamma/beta/scale/shift are
+// folded ONCE into y = x * a + b, then the thread streams over its pixels (4 loads in flight).
 __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x1, uint32_t C1, const __half* __restrict__ x2, uint32_t C2,
-                                                  uint32_t B, uint32_t HW, uint32_t groups, const float* __restrict__ stats,
+                                                  uint32_t HW, uint32_t groups, uint32_t pix_per_block, const float* __restrict__ stats,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   const float* __restrict__ scale_shift, long long ss_batch_stride, float eps, int do_silu,
                                                   __half* __restrict__ out) {
     const uint32_t C = C1 + C2, cv = C / 8, cv1 = C1 / 8;
-    const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;
-    if (i >= (size_t)B * HW * cv) return;
-    const uint32_t v = (uint32_t)(i % cv);
-    const size_t bp = i / cv;
-    const uint32_t b = (uint32_t)(bp / HW);
-    const __half* src = v < cv1 ? x1 + bp * C1 + v * 8 : x2 + bp * C2 + (v - cv1) * 8;
-    float f[8];
-    h8_to_f(__ldg(reinterpret_cast<const uint4*>(src)), f);
+    const uint32_t b = blockIdx.y;
+    const uint32_t v = threadIdx.x % cv, lane_p = threadIdx.x / cv, pstep = blockDim.x / cv;
     const uint32_t cpg = C / groups;
     const float inv_n = 1.0f / ((float)HW * (float)cpg);
     const float* ss = scale_shift ? scale_shift + (size_t)b * ss_batch_stride : nullptr;
-    uint32_t g_prev = 0xffffffffu;
-    float mean = 0.0f, rstd = 0.0f;
+    float a[8], bb[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t c = v * 8 + k, g = c / cpg;
-        if (g != g_prev) {
-            const float s = __ldg(stats + ((size_t)b * groups + g) * 2), q = __ldg(stats + ((size_t)b * groups + g) * 2 + 1);
-            mean = s * inv_n;
-            rstd = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.0f) + eps);
-            g_prev = g;
-        }
-        float y = (f[k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (ss) y = fmaf(y, 1.0f + __ldg(ss + c), __ldg(ss + C + c));
-        if (do_silu) y = silu_f(y);
-        f[k] = y;
+        const float sm = __ldg(stats + ((size_t)b * groups + g) * 2), sq = __ldg(stats + ((size_t)b * groups + g) * 2 + 1);
+        const float mean = sm * inv_n;
+        const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + eps);
+        float ak = rstd * __ldg(gamma + c);
+        float bk = __ldg(beta + c) - mean * ak;
+        if (ss) { const float sc = 1.0f + __ldg(ss + c); ak *= sc; bk = fmaf(bk, sc, __ldg(ss + C + c)); }
+        a[k] = ak; bb[k] = bk;
     }
-    reinterpret_cast<uint4*>(out)[i] = f_to_h8(f);
+    const __half* src = v < cv1 ? x1 + (size_t)b * HW * C1 + v * 8 : x2 + (size_t)b * HW * C2 + (v - cv1) * 8;
+    const uint32_t cs = v < cv1 ? C1 : C2;
+    __half* dst = out + (size_t)b * HW * C + v * 8;
+    const uint32_t p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+    auto emit = [&](const uint4& r, uint32_t p) {
+        float f[8];
+        h8_to_f(r, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { float y = fmaf(f[k], a[k], bb[k]); f[k] = do_silu ? silu_f(y) : y; }
+        *reinterpret_cast<uint4*>(dst + (size_t)p * C) = f_to_h8(f);
+    };
+    uint32_t p = p0 + lane_p;
+    for (; p + 3 * pstep < p1; p += 4 * pstep) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(p + u * pstep) * cs));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) emit(r[u], p + u * pstep);
+    }
+    for (; p < p1; p += pstep) emit(__ldg(reinterpret_cast<const uint4*>(src + (size_t)p * cs)), p);
 }
 
 // ---------------------------------------------------------------- stride-2 3x3 im2col: [B,H,W,C] -> [B,H/2,W/2,9C]
@@ -261,7 +285,7 @@ int ssdnerf_gn_stats(const void* x1, uint32_t C1, const void* x2, uint32_t C2, u
     if (!B || !HW) return 0;
     // enough blocks to fill the machine, at least 64 pixels per block
     uint32_t chunks = (HW + 63) / 64;
-    const uint32_t max_chunks = (148 * 4 + B - 1) / B;
+    const uint32_t max_chunks = (148 * 8 + B - 1) / B;
     if (chunks > max_chunks) chunks = max_chunks;
     const uint32_t ppb = (HW + chunks - 1) / chunks;
     chunks = (HW + ppb - 1) / ppb;
@@ -277,10 +301,17 @@ int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, uint32_t C2, u
     const uint32_t C = C1 + (x2 ? C2 : 0);
     if (C1 % 8 || (x2 && C2 % 8) || C % groups) return set_error_msg(SSDNERF_ERR_ARG, "gn_apply: channels must be multiples of 8 and of groups");
     CHK_ALIGN16(x1, "gn_apply"); CHK_ALIGN16(x2, "gn_apply"); CHK_ALIGN16(out, "gn_apply");
-    const size_t n = (size_t)B * HW * (C / 8);
-    if (!n) return 0;
-    k_gn_apply<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0, B, HW, groups, stats,
-                                                                    gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, (__half*)out);
+    if (!B || !HW) return 0;
+    const uint32_t cv = C / 8;
+    if (cv > 256) return set_error_msg(SSDNERF_ERR_ARG, "gn_apply: at most 2048 channels");
+    const uint32_t threads = cv * (256 / cv);
+    uint32_t chunks = (HW + 31) / 32;
+    const uint32_t max_chunks = (148 * 8 + B - 1) / B;
+    if (chunks > max_chunks) chunks = max_chunks;
+    const uint32_t ppb = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppb - 1) / ppb;
+    k_gn_apply<<<dim3(chunks, B), threads, 0, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0, HW, groups, ppb, stats,
+                                                                     gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, (__half*)out);
     SSDNERF_LAUNCH_OK();
     return 0;
 }

@@ -10,7 +10,9 @@ from . import _lib as N
 
 DEC_P = 0   # shipped configs: base 18->64, density 64->1, dir_net 16->64, color 64->3
 DEC_S = 1   # TriPlaneDecoder class defaults: base 96->128, density 128->1, color 144->128->3
-_VARIANT_C = {DEC_P: 6, DEC_S: 32}
+DEC_P_SIMT = 2   # DEC_P on the CUDA cores (plain fp32)
+DEC_P_TC = 3     # DEC_P with a split-precision tcgen05 base layer
+_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6}
 
 
 def detect_variant(params):
@@ -38,7 +40,7 @@ def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cu
     if variant is None:
         variant = detect_variant(params)
     p = {k: v.detach().float().cpu() for k, v in params.items()}
-    if variant == DEC_P:
+    if variant in (DEC_P, DEC_P_SIMT, DEC_P_TC):
         w1 = _plane_major(p['base_net.0.weight'], 6).t().contiguous()           # [18][64], row k = plane*6+c
         parts = [w1.reshape(-1), p['base_net.0.bias'],
                  p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),

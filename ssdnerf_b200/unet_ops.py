@@ -21,7 +21,7 @@ class GemmArgs(ctypes.Structure):
         ('taps', N.c_u32),
         ('b', N.c_void_p), ('b_strides', c_u64 * 3), ('n', N.c_u32), ('n_rows_b', N.c_u32), ('bx2', N.c_u32), ('bx3', N.c_u32),
         ('b_batched', N.c_u32),
-        ('bn', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
+        ('bn', N.c_u32), ('cluster', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
         ('out', N.c_void_p), ('out_f32', N.c_u32), ('so1', c_ll), ('so2', c_ll), ('so3', c_ll),
     ]
 
@@ -55,7 +55,7 @@ def pack_conv_weight(w, cin_pad=None):
     return _pad_rows(wp).contiguous()
 
 
-def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.0, bn=0, n=None):
+def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.0, bn=0, n=None, cluster=0):
     """out[M, N] = alpha * a[M, K] @ w[N, K]^T + bias + residual.  a fp16 [M, K] (row stride may exceed K)."""
     N.require_cuda(a, w)
     M, K = a.shape
@@ -71,7 +71,7 @@ def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.
     g.b, g.n, g.n_rows_b, g.bx2, g.bx3 = w.data_ptr(), n, w.shape[0], 1, 1
     ws = w.stride(0) * 2
     g.b_strides = (c_u64 * 3)(ws, ws * w.shape[0], ws * w.shape[0])
-    g.bn, g.alpha = bn, alpha
+    g.bn, g.alpha, g.cluster = bn, alpha, cluster
     g.bias_n = bias.data_ptr() if bias is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)
@@ -87,7 +87,7 @@ def _conv_boxes(H, W):
     return bw, bh, nb
 
 
-def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0):
+def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0, cluster=0):
     """3x3 (taps=9, pad 1, stride 1) or 1x1 (taps=1) convolution over NHWC fp16 x [B,H,W,C1] (+ x2 [B,H,W,C2] concatenated
     along channels).  wp: packed weight [taps][Cout_pad][C1+C2]."""
     N.require_cuda(x, wp)
@@ -110,7 +110,7 @@ def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f3
     rows = wp.shape[-2]
     g.b, g.n, g.n_rows_b, g.bx2, g.bx3 = wp.data_ptr(), cout, rows, taps, 1
     g.b_strides = (c_u64 * 3)(ktot * 2, rows * ktot * 2, taps * rows * ktot * 2)
-    g.bn, g.alpha = bn, 1.0
+    g.bn, g.alpha, g.cluster = bn, 1.0, cluster
     g.bias_n = bias.data_ptr() if bias is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)

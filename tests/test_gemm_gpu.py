@@ -66,3 +66,28 @@ def test_batched_attention_gemms(cuda):
     k = qkv.float().view(B, T, heads, 3, ch)[:, :, :, 1]
     ref = torch.einsum('bthc,bshc->bhts', q, k) * ch ** -0.5
     _check(S, ref, 1e-3)
+
+
+@pytest.mark.parametrize('cluster', [1, 2])
+@pytest.mark.parametrize('B,H,W,Cin,Cout,bn', [(3, 64, 64, 128, 256, 256), (2, 128, 128, 64, 128, 128), (5, 8, 8, 512, 512, 256), (1, 32, 32, 256, 256, 128)])
+def test_conv3x3_cluster_multicast(cuda, cluster, B, H, W, Cin, Cout, bn):
+    """CTA pairs along M with TMA multicast of the weight tile (odd tile counts exercise the zero-filled tail CTA)"""
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(B * H + Cin + cluster)
+    x = torch.randn(B, H, W, Cin, generator=g).half().to(cuda)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g).to(cuda)
+    res = torch.randn(B, H, W, Cout, generator=g).half().to(cuda)
+    out = U.conv3x3_f16(x, U.pack_conv_weight(w).to(cuda), Cout, bias=b, residual=res, bn=bn, cluster=cluster)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.half().float().to(cuda), b, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref)
+
+
+def test_plain_gemm_cluster(cuda):
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(77)
+    M, N, K = 128 * 7, 512, 576
+    a = (torch.randn(M, K, generator=g) * 0.5).half().to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.1).half().to(cuda)
+    out = U.linear_f16(a, w, bn=256, cluster=2)
+    _check(out, a.float() @ w.float().t())
