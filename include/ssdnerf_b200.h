@@ -141,6 +141,7 @@ typedef struct ssdnerf_render_args {
     int32_t* num_samples;     /* samples composited per ray, optional */
     int32_t* voxel_trace;     /* optional [B][N][trace_cap] occupancy-bit index of every composited sample (-1 padded) */
     uint32_t trace_cap;
+    void* debug_phase_cycles; /* optional uint64[8]: per-phase clock64 totals of thread 0 of every CTA (SSDNERF_DEC_P_TC only) */
     /* --- scratch */
     void* workspace;          /* >= ssdnerf_render_workspace_bytes(...) bytes, 16-byte aligned */
     size_t workspace_bytes;

@@ -32,4 +32,9 @@ for emu in (1,):
     ms = e0.elapsed_time(e1) / 5
     ns = out['num_samples'].sum().item()
     rays = B * V * res * res
+    if variant == 'P_TC':
+        prof = torch.zeros(8, dtype=torch.int64, device=dev)
+        R.render_fwd(vid, planes, (128, 128), bf, blob, poses=poses, intrinsics=intr, img_hw=(res, res), emulate_schedule=False, debug_phase_cycles=prof)
+        pc = prof.cpu().numpy()[:6].astype(float)
+        print('phase share [probe, gather, fence+bar, mma wait, heads, composite]:', (pc / pc.sum()).round(3), 'cycles per CTA-thread0 total', pc.sum() / (148 * 2))
     print(f'variant {variant} emulate={emu}: {ms:.3f} ms  rays/s={rays/ms*1e3:.3e}  samples={ns} samples/s={ns/ms*1e3:.3e} mean rgb={out["rgb"].mean().item():.4f}')

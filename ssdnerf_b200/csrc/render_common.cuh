@@ -23,6 +23,7 @@ struct RenderParams {
     uint32_t* hist; uint32_t hist_bins;
     uint32_t* budget;          // [B] emulated per-ray sample budget
     uint32_t hard_cap, max_steps;
+    unsigned long long* prof;  // optional [8] phase cycle counters (debug instrumentation; NULL in production)
     int patch_tiles;           // camera mode: a 32-ray tile is an 8x4 pixel patch instead of 32 consecutive pixels
 };
 

@@ -43,11 +43,10 @@ __global__ void k_pack_planes(const float* __restrict__ code, uint32_t B, uint32
 struct SmemP {
     float4 w1[DecP::KF][DecP::HID / 4];
     float4 wdir[16][DecP::HID / 4];
-    float b1[DecP::HID];
-    float wd[DecP::HID];
+    float4 b1[DecP::HID / 4];
+    float4 heads[DecP::HID];             // {wd, wc0, wc1, wc2}[o]: one broadcast 16-byte load per hidden unit
     float bdir[DecP::HID];
-    float wc[3][DecP::HID];
-    float dirf[DecP::HID][kCtaThreads];  // per-ray dir_net(SH16(d)) + b1 folded in; column = thread
+    float dirf[DecP::HID][kCtaThreads];  // per-ray dir_net(SH16(d)); column = thread
     float bd, bc[3], sat;
 };
 
@@ -61,7 +60,10 @@ __device__ __forceinline__ void decode_p(const SmemP& s, const float* __restrict
     gather_plane_p(planes + 2 * plane_stride, Hp, Wp, y, z, f + 12);// plane 2: (y, z)
     float acc[DecP::HID];
 #pragma unroll
-    for (int o = 0; o < DecP::HID; ++o) acc[o] = s.b1[o];
+    for (int o4 = 0; o4 < DecP::HID / 4; ++o4) {
+        const float4 b = s.b1[o4];
+        acc[4 * o4] = b.x; acc[4 * o4 + 1] = b.y; acc[4 * o4 + 2] = b.z; acc[4 * o4 + 3] = b.w;
+    }
 #pragma unroll
     for (int k = 0; k < DecP::KF; ++k) {
         const float fk = f[k];
@@ -79,11 +81,12 @@ __device__ __forceinline__ void decode_p(const SmemP& s, const float* __restrict
 #pragma unroll
     for (int o = 0; o < DecP::HID; ++o) {
         const float bx = acc[o];
-        sd = fmaf(silu_f(bx), s.wd[o], sd);
+        const float4 hw = s.heads[o];
+        sd = fmaf(silu_f(bx), hw.x, sd);
         const float h = silu_f(bx + s.dirf[o][tid]);
-        r = fmaf(h, s.wc[0][o], r);
-        g = fmaf(h, s.wc[1][o], g);
-        b = fmaf(h, s.wc[2][o], b);
+        r = fmaf(h, hw.y, r);
+        g = fmaf(h, hw.z, g);
+        b = fmaf(h, hw.w, b);
     }
     sigma = __expf(sd);
     const float k1 = 1.0f + 2.0f * s.sat;
@@ -107,12 +110,10 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_render_p(RenderParams p, int
         float* wdir = reinterpret_cast<float*>(s.wdir);
         for (int i = threadIdx.x; i < 16 * DecP::HID; i += kCtaThreads) wdir[i] = __ldg(blob + DecP::OFF_WDIR + i);
         for (int i = threadIdx.x; i < DecP::HID; i += kCtaThreads) {
-            s.b1[i] = __ldg(blob + DecP::OFF_B1 + i);
-            s.wd[i] = __ldg(blob + DecP::OFF_WD + i);
+            reinterpret_cast<float*>(s.b1)[i] = __ldg(blob + DecP::OFF_B1 + i);
             s.bdir[i] = __ldg(blob + DecP::OFF_BDIR + i);
-            s.wc[0][i] = __ldg(blob + DecP::OFF_WC + i);
-            s.wc[1][i] = __ldg(blob + DecP::OFF_WC + DecP::HID + i);
-            s.wc[2][i] = __ldg(blob + DecP::OFF_WC + 2 * DecP::HID + i);
+            s.heads[i] = make_float4(__ldg(blob + DecP::OFF_WD + i), __ldg(blob + DecP::OFF_WC + i),
+                                     __ldg(blob + DecP::OFF_WC + DecP::HID + i), __ldg(blob + DecP::OFF_WC + 2 * DecP::HID + i));
         }
         if (threadIdx.x == 0) {
             s.bd = __ldg(blob + DecP::OFF_BD);
@@ -327,6 +328,7 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
     p.min_near = a->min_near; p.T_thresh = a->T_thresh; p.bg_color = a->bg_color;
     p.weights_sum = a->weights_sum; p.depth = a->depth; p.image = a->image; p.rgb_blend = a->rgb_blend;
     p.voxel_trace = a->voxel_trace; p.trace_cap = a->trace_cap;
+    p.prof = (unsigned long long*)a->debug_phase_cycles;
     p.max_steps = a->max_steps;
     p.hard_cap = a->max_steps + 7;   // the reference's last quantum may overshoot max_steps by up to 7 samples
     p.hist_bins = a->max_steps + 9;

@@ -44,7 +44,7 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
     lo = __float2half_rn(x - __half2float(hi));
 }
 
-__global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int mode) {
+__global__ void __launch_bounds__(kPThreads, 2) k_render_ptc(RenderParams p, int mode) {
     extern __shared__ uint8_t smem_raw[];
     SmemPT& s = *reinterpret_cast<SmemPT*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,6 +96,10 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
     const uint32_t ahi = smem_u32(s.a_hi), alo = smem_u32(s.a_lo), whi_a = smem_u32(s.w_hi), wlo_a = smem_u32(s.w_lo);
     constexpr uint32_t idesc = make_idesc_f16(128, DecP::HID);
     uint32_t bar_phase = 0;
+    unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
+    const bool prof = p.prof != nullptr && tid == 0;
+#define PTC_T(i) do { if (prof) { const long long _n = clock64(); pc[i] += (unsigned long long)(_n - t_prev); t_prev = _n; } } while (0)
+    long long t_prev = clock64();
 
     const uint32_t warp_tiles_per_scene = div_up(p.rays_per_scene, 32u);
     const uint32_t cta_tiles_per_scene = div_up(warp_tiles_per_scene, 4u);
@@ -166,18 +170,21 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
                 has = probe(c, r, grid, t, x, y, z, dt, vi);
             }
             if (!__syncthreads_or(has)) break;
+            PTC_T(0);   // probe + vote
 
-            // ---- phase 2: cooperative gather -> split fp16 feature rows in shared memory
+            // ---- phase 2: cooperative gather -> split fp16 feature rows in shared memory.
+            // All 24 texel loads of the iteration are issued before any of them is consumed (one L2 round trip per iteration
+            // instead of twelve dependent ones): 2a fetch the sample positions, 2b issue loads, 2c blend / exchange / store.
             const uint32_t has_mask = __ballot_sync(0xffffffffu, has);
-#pragma unroll 1
+            float4 la[4][3], lc[4][3];
+            float w0s[4][3], w1s[4][3];
+#pragma unroll
             for (int round = 0; round < 4; ++round) {
                 const int src = round * 8 + quad;
                 const float sx = __shfl_sync(0xffffffffu, x, src);
                 const float sy = __shfl_sync(0xffffffffu, y, src);
                 const float sz = __shfl_sync(0xffffffffu, z, src);
                 const bool on = (has_mask >> src) & 1u;
-                const uint32_t row = (uint32_t)warp * 32u + (uint32_t)src;
-                const uint32_t row_off = (row >> 3) * kPA_SBO + (row & 7) * 16 + hh * 8;
 #pragma unroll
                 for (int pl = 0; pl < 3; ++pl) {
                     const float u = (pl == 2) ? sy : sx, v = (pl == 0) ? sy : sz;     // planes (x,y) (x,z) (y,z)
@@ -189,14 +196,27 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
                     const int x0 = (int)fx0, y0 = (int)fy0;
                     const int xsel = xs ? min(x0 + 1, Wm1) : x0, y1 = min(y0 + 1, Hm1);
                     const float wx = xs ? (ix - fx0) : ((fx0 + 1.0f) - ix);
-                    const float wy1 = iy - fy0, wy0 = (fy0 + 1.0f) - iy;
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), cc = a;
+                    w0s[round][pl] = wx * ((fy0 + 1.0f) - iy);
+                    w1s[round][pl] = wx * (iy - fy0);
+                    la[round][pl] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    lc[round][pl] = la[round][pl];
                     if (on) {
                         const float* base = planes + pl * plane_stride + hh * 4;
-                        a = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * p.plane_w + xsel) * DecP::CPAD));
-                        cc = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * p.plane_w + xsel) * DecP::CPAD));
+                        la[round][pl] = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * p.plane_w + xsel) * DecP::CPAD));
+                        lc[round][pl] = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * p.plane_w + xsel) * DecP::CPAD));
                     }
-                    const float w0 = wx * wy0, w1 = wx * wy1;
+                }
+            }
+#pragma unroll
+            for (int round = 0; round < 4; ++round) {
+                const int src = round * 8 + quad;
+                const bool on = (has_mask >> src) & 1u;
+                const uint32_t row = (uint32_t)warp * 32u + (uint32_t)src;
+                const uint32_t row_off = (row >> 3) * kPA_SBO + (row & 7) * 16 + hh * 8;
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    const float4 a = la[round][pl], cc = lc[round][pl];
+                    const float w0 = w0s[round][pl], w1 = w1s[round][pl];
                     float f0 = a.x * w0 + cc.x * w1, f1 = a.y * w0 + cc.y * w1, f2 = a.z * w0 + cc.z * w1, f3 = a.w * w0 + cc.w * w1;
                     f0 += __shfl_xor_sync(0xffffffffu, f0, 2);
                     f1 += __shfl_xor_sync(0xffffffffu, f1, 2);
@@ -215,9 +235,11 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
                     }
                 }
             }
+            PTC_T(1);   // gather + stores
             fence_proxy_async_smem();
             tc_fence_before();
             __syncthreads();
+            PTC_T(2);   // fence + barrier
 
             // ---- base layer on the tensor cores (3 split-precision products, K = 32 each)
             if (tid == 0) {
@@ -235,6 +257,7 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
             }
             mbar_wait(&s.mma_bar, bar_phase); bar_phase ^= 1;
             tc_fence_after();
+            PTC_T(3);   // MMA issue + completion wait
 
             // ---- heads in registers
             float sd = s.bd, o_r = s.bc[0], o_g = s.bc[1], o_b = s.bc[2];
@@ -253,6 +276,7 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
                 }
             }
             tc_fence_before();
+            PTC_T(4);   // TMEM loads + heads
 
             // ---- composite (raymarching.cu:865-897 arithmetic)
             if (has) {
@@ -270,6 +294,7 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
                 if (T < p.T_thresh) { alive = false; tbreak = true; }
                 else t = __fadd_rn(t, dt);
             }
+            PTC_T(5);   // composite
         }
         if (active) {
             p.weights_sum[gidx] = ws;
@@ -287,6 +312,7 @@ __global__ void __launch_bounds__(kPThreads, 3) k_render_ptc(RenderParams p, int
             }
         }
     }
+    if (prof) for (int i = 0; i < 6; ++i) atomicAdd(p.prof + i, pc[i]);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, kPTmemCols); }

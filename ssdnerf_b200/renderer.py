@@ -79,7 +79,7 @@ def pack_planes(code, variant):
 
 def render_fwd(variant, planes, plane_hw, bitfield, blob, rays_o=None, rays_d=None, poses=None, intrinsics=None,
                img_hw=None, grid_size=64, bound=1.0, min_near=0.2, max_steps=256, T_thresh=1e-4, bg_color=1.0,
-               dt_gamma=None, emulate_schedule=True, trace_cap=0, want_blend=True, want_counts=True):
+               dt_gamma=None, emulate_schedule=True, trace_cap=0, want_blend=True, want_counts=True, debug_phase_cycles=None):
     """One fused render of B scenes.
 
     Either explicit rays (rays_o, rays_d: [B,N,3]) or cameras (poses [B,V,4,4], intrinsics [B,V,4], img_hw).
@@ -124,6 +124,7 @@ def render_fwd(variant, planes, plane_hw, bitfield, blob, rays_o=None, rays_d=No
     a.weights_sum, a.depth, a.image = N.ptr(out['weights_sum']), N.ptr(out['depth']), N.ptr(out['image'])
     a.rgb_blend, a.num_samples = N.ptr(out['rgb']), N.ptr(out['num_samples'])
     a.voxel_trace, a.trace_cap = N.ptr(out['trace']), trace_cap
+    a.debug_phase_cycles = N.ptr(debug_phase_cycles)
     a.workspace, a.workspace_bytes = N.ptr(workspace), ws_bytes
     import ctypes
     N.check(N.lib().ssdnerf_render_fwd(ctypes.byref(a), N.stream_ptr()))
