@@ -97,7 +97,8 @@ SSDNERF_API int ssdnerf_sh_encode_backward(const float* grad, const float* input
                            (configs/paper_cfgs/ssdnerf_cars_uncond.py:40-51) */
 #define SSDNERF_DEC_P_SIMT 2 /* decoder P on the CUDA cores in plain fp32 (csrc/render_fused.cu) */
 #define SSDNERF_DEC_P_TC 3   /* decoder P with the base layer as a split-precision fp16 tcgen05 GEMM (csrc/render_ptc.cu);
-                                SSDNERF_DEC_P selects whichever of the two is currently faster */
+                                SSDNERF_DEC_P selects the fastest P kernel (currently SSDNERF_DEC_P_MMA) */
+#define SSDNERF_DEC_P_MMA 4  /* decoder P, warp-synchronous: per-warp split-precision mma.sync base layer (csrc/render_p2.cu) */
 #define SSDNERF_DEC_S 1 /* TriPlaneDecoder class defaults: base 3*32->128, density 128->1, color (128+16)->128->3
                            (lib/models/decoders/triplane_decoder.py:24-39) */
 

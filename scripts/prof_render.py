@@ -7,7 +7,7 @@ from ssdnerf_b200 import renderer as R
 from tests.common import spiral_poses
 dev = torch.device('cuda:0')
 variant = sys.argv[1]
-vid = {'P': R.DEC_P, 'P_TC': R.DEC_P_TC, 'S': R.DEC_S}[variant]
+vid = {'P': R.DEC_P, 'P_TC': R.DEC_P_TC, 'P_MMA': R.DEC_P_MMA, 'S': R.DEC_S}[variant]
 C = 32 if variant == 'S' else 6
 B, V = 4, 8
 g = torch.Generator().manual_seed(0)

@@ -64,6 +64,9 @@ __device__ __forceinline__ void make_ray(const RenderParams& p, uint32_t scene, 
 // variant P on tensor cores (render_ptc.cu)
 int render_ptc_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream);
 
+// variant P, warp-level mma.sync (render_p2.cu)
+int render_p2_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream);
+
 // variant S (render_tc.cu)
 size_t dec_s_blob_floats();
 int render_s_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream);

@@ -11,6 +11,7 @@
 // with weights broadcast from shared memory.  Variant S (3x32 channels, hidden 128) lives in
 // render_tc.cu (tcgen05 MMA, fp16 operands, fp32 accumulation in TMEM).
 #include "common.cuh"
+#include <cstdlib>
 #include "render_common.cuh"
 #include "dec_p.cuh"
 #include "../../include/ssdnerf_b200.h"
@@ -100,7 +101,8 @@ __device__ __forceinline__ void decode_p(const SmemP& s, const float* __restrict
 // mode 0: main pass (cap = max_steps + 7, builds the lifetime histogram)
 // mode 1: fix-up pass (only rays whose main-pass count exceeds the emulated budget are re-rendered)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCtaThreads, 3) k_render_p(RenderParams p, int mode) {
+template <int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB) k_render_p(RenderParams p, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemP& s = *reinterpret_cast<SmemP*>(smem_raw);
     {   // stage weights once per (persistent) CTA
@@ -260,14 +262,14 @@ using namespace ssdnerf;
 extern "C" {
 
 size_t ssdnerf_decoder_blob_floats(int variant) {
-    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC) return DecP::BLOB;
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) return DecP::BLOB;
     if (variant == SSDNERF_DEC_S) return ssdnerf::dec_s_blob_floats();
     return 0;
 }
 
 size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp) {
     const size_t texels = (size_t)B * 3 * Hp * Wp;
-    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC) return texels * 8 * sizeof(float);
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) return texels * 8 * sizeof(float);
     if (variant == SSDNERF_DEC_S) return texels * 32 * sizeof(__half);
     return 0;
 }
@@ -278,7 +280,7 @@ int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, 
     if (total == 0) return 0;
     if (((uintptr_t)planes & 15u) != 0) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: planes must be 16-byte aligned");
     const uint32_t blocks = (uint32_t)((total + 255) / 256);
-    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC) {
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) {
         if (C != 6) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: variant P expects 6 channels per plane");
         k_pack_planes<float, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(code, B, C, Hp, Wp, (float*)planes);
     } else if (variant == SSDNERF_DEC_S) {
@@ -349,23 +351,29 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
     if (a->variant == SSDNERF_DEC_P_TC) return ssdnerf::render_ptc_launch(p, a->emulate_schedule, hist, sms, stream);
-    if (a->variant == SSDNERF_DEC_P || a->variant == SSDNERF_DEC_P_SIMT) {
+    if (a->variant == SSDNERF_DEC_P_MMA || a->variant == SSDNERF_DEC_P) return ssdnerf::render_p2_launch(p, a->emulate_schedule, hist, sms, stream);
+    if (a->variant == SSDNERF_DEC_P_SIMT) {
+        // two register budgets of the same kernel: 3 CTAs/SM (168 regs, no spills) or 4 CTAs/SM (128 regs, small spills);
+        // SSDNERF_P_OCC=3|4 overrides the default for A/B runs
+        static int occ_choice = 0;
+        if (!occ_choice) { const char* e = getenv("SSDNERF_P_OCC"); occ_choice = (e && e[0] == '4') ? 4 : 3; }
         const size_t smem = sizeof(SmemP);
-        static bool attr_set = false;
-        if (!attr_set) {
-            SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_render_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
+        auto kern = occ_choice == 3 ? k_render_p<3> : k_render_p<4>;
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[occ_choice - 3]) {
+            SSDNERF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[occ_choice - 3] = true;
         }
         int occ = 0;
-        SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_p, kCtaThreads, smem));
+        SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem));
         if (occ < 1) return set_error_msg(SSDNERF_ERR_CUDA, "render_fwd: kernel does not fit on this device");
         const uint32_t total_tiles = div_up(a->rays_per_scene, 32u) * a->num_scenes;
         const uint32_t grid = (uint32_t)min((uint64_t)sms * occ, (uint64_t)div_up(total_tiles, kWarpsPerCta));
-        k_render_p<<<grid, kCtaThreads, smem, stream>>>(p, 0);
+        kern<<<grid, kCtaThreads, smem, stream>>>(p, 0);
         SSDNERF_LAUNCH_OK();
         if (a->emulate_schedule) {
             if (int e = launch_schedule(hist, p.hist_bins, a->num_scenes, a->rays_per_scene, a->max_steps, p.budget, stream)) return e;
-            k_render_p<<<grid, kCtaThreads, smem, stream>>>(p, 1);
+            kern<<<grid, kCtaThreads, smem, stream>>>(p, 1);
             SSDNERF_LAUNCH_OK();
         }
         return 0;

@@ -12,7 +12,8 @@ DEC_P = 0   # shipped configs: base 18->64, density 64->1, dir_net 16->64, color
 DEC_S = 1   # TriPlaneDecoder class defaults: base 96->128, density 128->1, color 144->128->3
 DEC_P_SIMT = 2   # DEC_P on the CUDA cores (plain fp32)
 DEC_P_TC = 3     # DEC_P with a split-precision tcgen05 base layer
-_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6}
+DEC_P_MMA = 4    # DEC_P, warp-synchronous split-precision mma.sync base layer
+_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6, DEC_P_MMA: 6}
 
 
 def detect_variant(params):
@@ -40,7 +41,7 @@ def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cu
     if variant is None:
         variant = detect_variant(params)
     p = {k: v.detach().float().cpu() for k, v in params.items()}
-    if variant in (DEC_P, DEC_P_SIMT, DEC_P_TC):
+    if variant in (DEC_P, DEC_P_SIMT, DEC_P_TC, DEC_P_MMA):
         w1 = _plane_major(p['base_net.0.weight'], 6).t().contiguous()           # [18][64], row k = plane*6+c
         parts = [w1.reshape(-1), p['base_net.0.bias'],
                  p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),
