@@ -195,6 +195,9 @@ typedef struct ssdnerf_gemm_args {
     const float* bias_n;      /* [n] fp32 or NULL */
     const void* residual;     /* fp16, addressed like out, or NULL */
     void* out; uint32_t out_f32; long long so1, so2, so3; /* element strides of d1, d2, d3; columns contiguous */
+    /* optional fused GroupNorm statistics of the output: qstats [images][n/4][2] += {sum, sum of squares} of every 4-channel quad
+     * (caller zero-fills); image of a row = index along d3 (stats_hw == 0) or (index along d1) / stats_hw (flattened rows) */
+    float* qstats; uint32_t stats_hw;
 } ssdnerf_gemm_args;
 SSDNERF_API int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
 
@@ -206,6 +209,11 @@ SSDNERF_API int ssdnerf_nchw_to_nhwc_f16(const float* x, uint32_t B, uint32_t C,
  * and SiLU; writes the concatenated fp16 result. */
 SSDNERF_API int ssdnerf_gn_stats(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups,
                                  float* stats, void* stream);
+/* same as ssdnerf_gn_apply with the statistics given per 4-channel quad (as emitted by ssdnerf_gemm_f16's qstats):
+ * q1 [B][C1/4][2], q2 [B][C2/4][2] */
+SSDNERF_API int ssdnerf_gn_apply_q(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups,
+                                   const float* q1, const float* q2, const float* gamma, const float* beta, const float* scale_shift,
+                                   long long ss_batch_stride, float eps, int do_silu, void* out, void* stream);
 SSDNERF_API int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups,
                                  const float* stats, const float* gamma, const float* beta, const float* scale_shift,
                                  long long ss_batch_stride, float eps, int do_silu, void* out, void* stream);

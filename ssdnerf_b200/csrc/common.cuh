@@ -180,7 +180,11 @@ __device__ __forceinline__ void sh16(float x, float y, float z, float* o) {
     o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// SiLU / sigmoid as exactly {FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL}: the library forms (__expf, __fdividef) add range checks
+// (FSETP / extra FMULs) that cost issue slots in the MUFU-bound head loops.  exp(-x) overflowing to +inf gives rcp(inf) = 0: fine.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 
 }  // namespace ssdnerf

@@ -41,6 +41,8 @@ struct GemmParams {
     void* out;
     uint32_t out_f32;
     long long so1, so2, so3;    // output element strides of d1, d2, d3 (column stride 1)
+    float* qstats;              // optional [images][n_valid/4][2]: per-image sum / sum-of-squares of every 4-channel quad of the output
+    uint32_t stats_hw;          // > 0: image index of a row = (row index along d1) / stats_hw; 0: image index = index along d3
 };
 
 template <int BN>
@@ -49,7 +51,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*quad-stat accumulators*/;
 };
 
 // CL = cluster size along M: the CL CTAs of a cluster work on CL consecutive M tiles of the same N tile; each loads 1/CL of the
@@ -68,6 +70,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     uint64_t* tfull = empty + Cfg::kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* qacc = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [2 images][BN/4][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
@@ -86,6 +89,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    for (int i = threadIdx.x; i < BN; i += kGemmThreads) qacc[i] = 0.0f;     // 2 * BN/4 * 2 floats
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();       // peers' barriers are initialised before any multicast load / remote arrive targets them
@@ -158,6 +162,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
             const uint32_t g1 = t1 * p.b1 + i1, g2 = t2 * p.b2 + i2, g3 = t3 * p.b3 + i3;
             const bool row_ok = m_tile < tiles_m && g1 < p.d1 && g2 < p.d2 && g3 < p.d3;
             const long long off = (long long)g1 * p.so1 + (long long)g2 * p.so2 + (long long)g3 * p.so3 + (long long)n_tile * BN;
+            // GroupNorm quad statistics: image of this thread's row (warp-uniform) relative to the image of the tile's first row
+            const uint32_t img = p.stats_hw ? g1 / p.stats_hw : g3;
+            const uint32_t img0 = p.stats_hw ? (t1 * p.b1) / p.stats_hw : t3 * p.b3;
+            const uint32_t slot = (img - img0) & 1u;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -166,8 +174,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                 tmem_ld32(tmem_base + ((q * 32u) << 16) + acc * BN + c0, v);
                 tmem_ld_wait();
                 const uint32_t ncol0 = n_tile * BN + c0;
-                if (row_ok && ncol0 < p.n_valid) {
-                    float f[32];
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = 0.0f;
+                const bool live = row_ok && ncol0 < p.n_valid;
+                if (live) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
                     if (p.bias_n) {
@@ -213,9 +224,53 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                         }
                     }
                 }
+                if (p.qstats) {   // fused GroupNorm statistics of the (fp16-rounded) output: 8 quads x {sum, sumsq} per thread ...
+                    float sv[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        float su = 0.0f, sq = 0.0f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float x = f[4 * q4 + e];
+                            if (!p.out_f32) x = __half2float(__float2half_rn(x));
+                            if (!live || ncol0 + 4 * q4 + e >= p.n_valid) x = 0.0f;
+                            su += x; sq = fmaf(x, x, sq);
+                        }
+                        sv[q4] = su; sv[8 + q4] = sq;
+                    }
+                    // ... reduce-scattered over the warp's 32 rows with 16 shuffles: lane bits 4..1 select which of the 16 values it ends with
+#pragma unroll
+                    for (int m = 16, half = 8; m >= 2; m >>= 1, half >>= 1) {
+                        const bool upper = (lane & m) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const float send = upper ? sv[i] : sv[i + half];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, m);
+                            sv[i] = (upper ? sv[i + half] : sv[i]) + recv;
+                        }
+                    }
+                    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                    if ((lane & 1) == 0) {
+                        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        atomicAdd(qacc + (slot * (BN / 4) + c0 / 4 + (idx & 7)) * 2 + (idx >> 3), sv[0]);
+                    }
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
+            if (p.qstats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t et = threadIdx.x - 64;                 // 0..127 within the epilogue warps
+                const uint32_t nq = p.n_valid / 4;
+                for (uint32_t i = et; i < (uint32_t)BN; i += 128) {      // i = (slot * BN/4 + quad) * 2 + stat
+                    const float val = qacc[i];
+                    const uint32_t sl = i / (BN / 2), qd = (i % (BN / 2)) >> 1, st = i & 1u;
+                    const uint32_t gq = n_tile * (BN / 4) + qd;
+                    if (val != 0.0f && gq < nq) atomicAdd(p.qstats + ((size_t)(img0 + sl) * nq + gq) * 2 + st, val);
+                    qacc[i] = 0.0f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -331,6 +386,9 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     p.taps = a->taps; p.kc1 = a->k1 / 64; p.kc2 = a->a2 ? a->k2 / 64 : 0; p.n_valid = a->n; p.b_batched = a->b_batched;
     p.alpha = a->alpha; p.bias_n = a->bias_n; p.residual = (const __half*)a->residual; p.out = a->out; p.out_f32 = a->out_f32;
     p.so1 = a->so1; p.so2 = a->so2; p.so3 = a->so3;
+    p.qstats = a->qstats; p.stats_hw = a->stats_hw;
+    if (a->qstats && (a->n % 4)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: quad statistics need n % 4 == 0");
+    if (a->qstats && a->stats_hw && (a->stats_hw % 64)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: stats_hw must be a multiple of 64");
     const uint64_t ktot = (uint64_t)a->k1 + (a->a2 ? a->k2 : 0);
 
     CUtensorMap mA1, mA2, mB;

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x1,
 // folded ONCE into y = x * a + b, then the thread streams over its pixels (4 loads in flight).
 __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x1, uint32_t C1, const __half* __restrict__ x2, uint32_t C2,
                                                   uint32_t HW, uint32_t groups, uint32_t pix_per_block, const float* __restrict__ stats,
-                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float* __restrict__ stats2, int quad_stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   const float* __restrict__ scale_shift, long long ss_batch_stride, float eps, int do_silu,
                                                   __half* __restrict__ out) {
     const uint32_t C = C1 + C2, cv = C / 8, cv1 = C1 / 8;
@@ -111,7 +111,17 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x1,
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t c = v * 8 + k, g = c / cpg;
-        const float sm = __ldg(stats + ((size_t)b * groups + g) * 2), sq = __ldg(stats + ((size_t)b * groups + g) * 2 + 1);
+        float sm, sq;
+        if (!quad_stats) {
+            sm = __ldg(stats + ((size_t)b * groups + g) * 2); sq = __ldg(stats + ((size_t)b * groups + g) * 2 + 1);
+        } else {   // sum the group's 4-channel quads; quads [0, C1/4) come from source 1, the rest from source 2
+            sm = 0.0f; sq = 0.0f;
+            const uint32_t q1n = C1 / 4, q2n = C2 / 4;
+            for (uint32_t qi = g * (cpg / 4); qi < (g + 1) * (cpg / 4); ++qi) {
+                const float* src_q = qi < q1n ? stats + ((size_t)b * q1n + qi) * 2 : stats2 + ((size_t)b * q2n + (qi - q1n)) * 2;
+                sm += __ldg(src_q); sq += __ldg(src_q + 1);
+            }
+        }
         const float mean = sm * inv_n;
         const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + eps);
         float ak = rstd * __ldg(gamma + c);
@@ -295,9 +305,9 @@ int ssdnerf_gn_stats(const void* x1, uint32_t C1, const void* x2, uint32_t C2, u
     return 0;
 }
 
-int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups, const float* stats,
-                     const float* gamma, const float* beta, const float* scale_shift, long long ss_batch_stride, float eps, int do_silu,
-                     void* out, void* stream) {
+static int gn_apply_impl(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups, const float* stats,
+                         const float* stats2, int quad, const float* gamma, const float* beta, const float* scale_shift,
+                         long long ss_batch_stride, float eps, int do_silu, void* out, void* stream) {
     const uint32_t C = C1 + (x2 ? C2 : 0);
     if (C1 % 8 || (x2 && C2 % 8) || C % groups) return set_error_msg(SSDNERF_ERR_ARG, "gn_apply: channels must be multiples of 8 and of groups");
     CHK_ALIGN16(x1, "gn_apply"); CHK_ALIGN16(x2, "gn_apply"); CHK_ALIGN16(out, "gn_apply");
@@ -311,9 +321,25 @@ int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, uint32_t C2, u
     const uint32_t ppb = (HW + chunks - 1) / chunks;
     chunks = (HW + ppb - 1) / ppb;
     k_gn_apply<<<dim3(chunks, B), threads, 0, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0, HW, groups, ppb, stats,
-                                                                     gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, (__half*)out);
+                                                                     stats2, quad, gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, (__half*)out);
     SSDNERF_LAUNCH_OK();
     return 0;
+}
+
+int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups, const float* stats,
+                     const float* gamma, const float* beta, const float* scale_shift, long long ss_batch_stride, float eps, int do_silu,
+                     void* out, void* stream) {
+    return gn_apply_impl(x1, C1, x2, C2, B, HW, groups, stats, nullptr, 0, gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, out, stream);
+}
+
+int ssdnerf_gn_apply_q(const void* x1, uint32_t C1, const void* x2, uint32_t C2, uint32_t B, uint32_t HW, uint32_t groups, const float* q1,
+                       const float* q2, const float* gamma, const float* beta, const float* scale_shift, long long ss_batch_stride, float eps,
+                       int do_silu, void* out, void* stream) {
+    const uint32_t C = C1 + (x2 ? C2 : 0);
+    if (groups == 0 || C % groups || (C / groups) % 4 || C1 % 4 || (x2 && C2 % 4))
+        return set_error_msg(SSDNERF_ERR_ARG, "gn_apply_q: channels per group and per source must be multiples of 4");
+    if (!q1 || (x2 && !q2)) return set_error_msg(SSDNERF_ERR_ARG, "gn_apply_q: quad statistics missing");
+    return gn_apply_impl(x1, C1, x2, C2, B, HW, groups, q1, q2, 1, gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, out, stream);
 }
 
 int ssdnerf_im2col_s2(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream) {

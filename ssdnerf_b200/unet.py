@@ -251,8 +251,12 @@ class UNetEngine:
         self.out_seq = [[layer(p) for p in blk] for blk in m.out_blocks]
         self.out_norm = dict(g=f32(m.out.gn.weight), b=f32(m.out.gn.bias), n=self._norm_slot(), c=m.out.gn.num_channels)
         self.out_conv = dict(w=U.pack_conv_weight(m.out.conv.weight).to(dev), b=f32(m.out.conv.bias), cout=m.out.conv.out_channels)
-        # ---- GroupNorm statistics arena (zeroed once per forward) and scale/shift row (one per sample)
-        self.stats = torch.zeros(self.n_norm, batch, 32, 2, dtype=torch.float32, device=dev)
+        # ---- GroupNorm quad-statistics arena: one [B, C/4, 2] slice per tensor that feeds a norm, filled by the producing GEMM's
+        #      epilogue; zeroed once per forward (a single memset node in the captured graph)
+        self.qarena = torch.zeros(4 * 1024 * 1024, dtype=torch.float32, device=dev)
+        self.qoff = 0
+        self.qslots = {}
+        self._legacy_idx = 0
         self.ss_offsets, off = [], 0
         for d in self.res_blocks:
             self.ss_offsets.append(off)
@@ -284,38 +288,62 @@ class UNetEngine:
         self.ss_cur.copy_(self.scale_shift_rows(emb))
 
     # ------------------------------------------------------------------ kernels
-    def _gn(self, slot, x1, x2, gamma, beta, out, silu, ss_off=None):
+    def _q(self, key, channels):
+        """quad-statistics slice [B, C/4, 2] for the tensor produced at `key` (stable across forwards: graph-capturable)"""
+        t = self.qslots.get(key)
+        if t is None:
+            n = self.B * (channels // 4) * 2
+            t = self.qarena[self.qoff:self.qoff + n].view(self.B, channels // 4, 2)
+            self.qoff += (n + 63) // 64 * 64
+            assert self.qoff <= self.qarena.numel()
+            self.qslots[key] = t
+        return t
+
+    def _gn(self, x1, q1, x2, q2, gamma, beta, out, silu, ss_off=None):
+        """GroupNorm(32) over the channel concat of x1 (+x2) from the quad statistics their producers emitted"""
         B, H, W, C1 = x1.shape
         C2 = x2.shape[-1] if x2 is not None else 0
-        st = self.stats[slot]
         L, s = N.lib(), N.stream_ptr()
-        N.check(L.ssdnerf_gn_stats(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st), s))
         ss = None
         if ss_off is not None:
             ss = N.c_void_p(self.ss_cur.data_ptr() + 4 * ss_off)
-        N.check(L.ssdnerf_gn_apply(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st),
-                                   N.ptr(gamma), N.ptr(beta), ss, N.c_longlong(self.ss_total), N.c_f32(1e-5), N.c_int(int(silu)),
-                                   N.ptr(out), s))
+        if ((C1 + C2) // 32) % 4 != 0:
+            # fewer than 4 channels per group (only sub-128-channel toy configs): separate statistics pass over group sums
+            self._legacy_idx += 1          # one slot per call site, in call order (stable across forwards)
+            st = self._q(('legacy', self._legacy_idx), 32 * 4)     # [B, 32, 2], contiguous
+            N.check(L.ssdnerf_gn_stats(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st), s))
+            N.check(L.ssdnerf_gn_apply(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st),
+                                       N.ptr(gamma), N.ptr(beta), ss, N.c_longlong(self.ss_total), N.c_f32(1e-5), N.c_int(int(silu)),
+                                       N.ptr(out), s))
+            return out
+        N.check(L.ssdnerf_gn_apply_q(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(q1),
+                                     N.ptr(q2), N.ptr(gamma), N.ptr(beta), ss, N.c_longlong(self.ss_total), N.c_f32(1e-5),
+                                     N.c_int(int(silu)), N.ptr(out), s))
         return out
 
     def _res(self, d, x, skip, tag):
+        """x, skip: (tensor, quad-stats) pairs; returns the block output with the stats its epilogue emitted"""
+        (x, qx), (sk, qs) = x, (skip if skip is not None else (None, None))
         B, H, W, _ = x.shape
         cin, cout = d['cin'], d['cout']
-        a = self._gn(d['n1'], x, skip, d['g1'], d['b1'], self._buf(('a', H, cin), (B, H, W, cin)), True)
-        h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', H, cout), (B, H, W, cout)))
-        a2 = self._gn(d['n2'], h1, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
+        a = self._gn(x, qx, sk, qs, d['g1'], d['b1'], self._buf(('a', H, cin), (B, H, W, cin)), True)
+        qh1 = self._q(('h1', tag), cout)
+        h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', H, cout), (B, H, W, cout)), qstats=qh1)
+        a2 = self._gn(h1, qh1, None, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
         if 'ws' in d:
-            sc = U.conv3x3_f16(x, d['ws'].unsqueeze(0), cout, bias=d['wsb'], x2=skip, taps=1, out=self._buf(('sc', H, cout), (B, H, W, cout)))
+            sc = U.conv3x3_f16(x, d['ws'].unsqueeze(0), cout, bias=d['wsb'], x2=sk, taps=1, out=self._buf(('sc', H, cout), (B, H, W, cout)))
         else:
             sc = x
-        return U.conv3x3_f16(a2, d['w2'], cout, bias=d['c2b'], residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)))
+        qo = self._q(('res_out', tag), cout)
+        return U.conv3x3_f16(a2, d['w2'], cout, bias=d['c2b'], residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)), qstats=qo), qo
 
     def _attn(self, d, x, tag):
+        x, qx = x
         B, H, W, c = x.shape
         T, heads = H * W, d['heads']
         ch = c // heads
         L, s = N.lib(), N.stream_ptr()
-        xn = self._gn(d['n'], x, None, d['g'], d['b'], self._buf(('xn', T, c), (B, H, W, c)), False)
+        xn = self._gn(x, qx, None, None, d['g'], d['b'], self._buf(('xn', T, c), (B, H, W, c)), False)
         qkv = U.linear_f16(xn.view(B * T, c), d['wqkv'], bias=d['bqkv'], n=3 * c, out=self._buf(('qkv', T, c), (B * T, 3 * c)))
         S = U.attn_scores(qkv.view(B, T, 3 * c), heads, scale=1.0 / math.sqrt(ch), out=self._buf(('S', T), (B, heads, T, T), torch.float32))
         P = self._buf(('P', T), (B, heads, T, T))
@@ -323,21 +351,27 @@ class UNetEngine:
         vt = self._buf(('vt', T, c), (B, heads, ch, T))
         N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
         o = U.attn_pv(P, vt, out=self._buf(('o', T, c), (B, T, c)))
+        qo = self._q(('attn_out', tag), c)
         return U.linear_f16(o.view(B * T, c), d['wproj'], bias=d['bproj'], residual=x.view(B * T, c), n=c,
-                            out=self._buf(('attn_out', tag), (B * T, c))).view(B, H, W, c)
+                            out=self._buf(('attn_out', tag), (B * T, c)), qstats=qo, stats_hw=T).view(B, H, W, c), qo
 
     def _down(self, d, x, tag):
+        x, _ = x
         B, H, W, c = x.shape
         col = self._buf(('col', H, c), (B, H // 2, W // 2, 9 * c))
         N.check(N.lib().ssdnerf_im2col_s2(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(col), N.stream_ptr()))
         M = B * (H // 2) * (W // 2)
-        return U.linear_f16(col.view(M, 9 * c), d['w'], bias=d['b'], n=c, out=self._buf(('down_out', tag), (M, c))).view(B, H // 2, W // 2, c)
+        qo = self._q(('down_out', tag), c)
+        return U.linear_f16(col.view(M, 9 * c), d['w'], bias=d['b'], n=c, out=self._buf(('down_out', tag), (M, c)), qstats=qo,
+                            stats_hw=(H // 2) * (W // 2)).view(B, H // 2, W // 2, c), qo
 
     def _up(self, d, x, tag):
+        x, _ = x
         B, H, W, c = x.shape
         up = self._buf(('upx', H, c), (B, 2 * H, 2 * W, c))
         N.check(N.lib().ssdnerf_upsample2x(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(up), N.stream_ptr()))
-        return U.conv3x3_f16(up, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)))
+        qo = self._q(('up_out', tag), c)
+        return U.conv3x3_f16(up, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)), qstats=qo), qo
 
     def _run(self, layers, h, skip, tag):
         for li, (kind, d) in enumerate(layers):
@@ -356,9 +390,11 @@ class UNetEngine:
     # ------------------------------------------------------------------ forward
     def forward_nhwc(self):
         """x_in (self.x_in, fp16 NHWC padded) -> self.v_out (fp32 NHWC); all launches on the current stream, capture-safe."""
-        self.stats.zero_()
-        h = U.conv3x3_f16(self.x_in, self.conv_in['w'], self.conv_in['cout'], bias=self.conv_in['b'],
-                          out=self._buf(('conv_in',), (self.B, self.H, self.W, self.conv_in['cout'])))
+        self.qarena[:max(self.qoff, 1)].zero_()
+        self._legacy_idx = 0
+        q0 = self._q(('conv_in',), self.conv_in['cout'])
+        h = (U.conv3x3_f16(self.x_in, self.conv_in['w'], self.conv_in['cout'], bias=self.conv_in['b'],
+                           out=self._buf(('conv_in',), (self.B, self.H, self.W, self.conv_in['cout'])), qstats=q0), q0)
         hs = [h]
         for i, layers in enumerate(self.in_seq):
             h = self._run(layers, h, None, ('in', i))
@@ -366,8 +402,9 @@ class UNetEngine:
         h = self._run(self.mid_seq, h, None, ('mid',))
         for j, layers in enumerate(self.out_seq):
             h = self._run(layers, h, hs.pop(), ('out', j))
+        h, qh = h
         B, H, W, c = h.shape
-        a = self._gn(self.out_norm['n'], h, None, self.out_norm['g'], self.out_norm['b'], self._buf(('a', H, c), (B, H, W, c)), True)
+        a = self._gn(h, qh, None, None, self.out_norm['g'], self.out_norm['b'], self._buf(('a', H, c), (B, H, W, c)), True)
         U.conv3x3_f16(a, self.out_conv['w'], self.out_conv['cout'], bias=self.out_conv['b'], out=self.v_out)
         return self.v_out
 

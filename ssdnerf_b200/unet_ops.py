@@ -23,6 +23,7 @@ class GemmArgs(ctypes.Structure):
         ('b_batched', N.c_u32),
         ('bn', N.c_u32), ('cluster', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
         ('out', N.c_void_p), ('out_f32', N.c_u32), ('so1', c_ll), ('so2', c_ll), ('so3', c_ll),
+        ('qstats', N.c_void_p), ('stats_hw', N.c_u32),
     ]
 
 
@@ -55,7 +56,7 @@ def pack_conv_weight(w, cin_pad=None):
     return _pad_rows(wp).contiguous()
 
 
-def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.0, bn=0, n=None, cluster=0):
+def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.0, bn=0, n=None, cluster=0, qstats=None, stats_hw=0):
     """out[M, N] = alpha * a[M, K] @ w[N, K]^T + bias + residual.  a fp16 [M, K] (row stride may exceed K)."""
     N.require_cuda(a, w)
     M, K = a.shape
@@ -76,6 +77,8 @@ def linear_f16(a, w, bias=None, residual=None, out=None, out_f32=False, alpha=1.
     g.residual = residual.data_ptr() if residual is not None else None
     g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)
     g.so1, g.so2, g.so3 = out.stride(0), 0, 0
+    if qstats is not None:
+        g.qstats, g.stats_hw = qstats.data_ptr(), stats_hw
     _launch(g)
     return out
 
@@ -87,7 +90,7 @@ def _conv_boxes(H, W):
     return bw, bh, nb
 
 
-def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0, cluster=0):
+def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0, cluster=0, qstats=None):
     """3x3 (taps=9, pad 1, stride 1) or 1x1 (taps=1) convolution over NHWC fp16 x [B,H,W,C1] (+ x2 [B,H,W,C2] concatenated
     along channels).  wp: packed weight [taps][Cout_pad][C1+C2]."""
     N.require_cuda(x, wp)
@@ -116,6 +119,8 @@ def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f3
     g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)
     co = out.shape[-1]
     g.so1, g.so2, g.so3 = co, W * co, H * W * co
+    if qstats is not None:
+        g.qstats, g.stats_hw = qstats.data_ptr(), 0
     _launch(g)
     return out
 

@@ -76,8 +76,10 @@ def test_attention_block_matches_oracle(cuda):
     assert kind == 'attn'
     g = torch.Generator().manual_seed(4)
     x = torch.randn(2, 128, 8, 8, generator=g)
-    eng.stats.zero_()
-    y = eng._attn(d, x.permute(0, 2, 3, 1).contiguous().half().to(cuda), ('t',))
+    xh = x.permute(0, 2, 3, 1).contiguous().half().to(cuda)
+    xq = xh.float().view(2, 64, 32, 4)                 # quad statistics the producing GEMM epilogue would have emitted
+    q = torch.stack([xq.sum(dim=(1, 3)), (xq * xq).sum(dim=(1, 3))], dim=-1).contiguous()
+    y, _ = eng._attn(d, (xh, q), ('t',))
     ref = up.attention(sd, dict(key='mid_blocks.1', c=128), x.half().float(), 2)
     assert _rel_l2(y.float().cpu().permute(0, 3, 1, 2), ref) < 3e-3
 
@@ -136,3 +138,25 @@ def test_full_unet_one_step_vs_oracle(cuda):
     err = _rel_l2(out, ref)
     print('full unet rel l2', err)
     assert err < 3e-3
+
+
+def test_fused_quad_stats_match_tensor(cuda):
+    """GroupNorm statistics emitted by the GEMM epilogue (conv, 8x8 two-images-per-tile conv, flattened-row GEMM) == sums of the output"""
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(31)
+    for (B, H, Cin, Cout) in [(3, 32, 128, 256), (5, 8, 256, 512), (2, 64, 64, 128)]:
+        x = torch.randn(B, H, H, Cin, generator=g).half().to(cuda)
+        w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05
+        q = torch.zeros(B, Cout // 4, 2, device=cuda)
+        out = U.conv3x3_f16(x, U.pack_conv_weight(w).to(cuda), Cout, qstats=q)
+        o = out.float().view(B, H * H, Cout // 4, 4)
+        ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+        torch.testing.assert_close(q, ref, rtol=2e-3, atol=2e-2)
+    B, T, c = 3, 64, 512
+    a = torch.randn(B * T, c, generator=g).half().to(cuda)
+    wl = U.pack_linear_weight(torch.randn(c, c, generator=g) * 0.05).to(cuda)
+    q = torch.zeros(B, c // 4, 2, device=cuda)
+    out = U.linear_f16(a, wl, n=c, qstats=q, stats_hw=T)
+    o = out.float().view(B, T, c // 4, 4)
+    ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    torch.testing.assert_close(q, ref, rtol=2e-3, atol=2e-2)
