@@ -30,3 +30,23 @@ def test_get_density_matches_oracle(cuda, grid_dtype):
     diff = np.unpackbits(bf.cpu().numpy() ^ bf_ref, axis=-1).sum()
     assert diff <= 1e-4 * B * 64 ** 3, diff
     assert 0.02 < np.unpackbits(bf_ref).mean() < 0.98
+
+
+def test_get_density_variant_S(cuda):
+    """class-default decoder (3x32 fp16 planes, hidden 128): grid values within fp16 tolerance of the fp32 oracle"""
+    from ssdnerf_b200 import renderer as R, density as D
+    g = torch.Generator().manual_seed(22)
+    code = torch.randn(1, 3, 32, 128, 128, generator=g).clamp(-2, 2)
+    params = rp.make_decoder_params('S', 6)
+    params['density_net.0.bias'] = params['density_net.0.bias'] - 2.0
+    rands = [torch.rand(64 ** 3, 3, generator=g) for _ in range(2)]
+    grid_ref, bf_ref = rp.get_density(params, code, rands, density_thresh=0.1, grid_dtype=torch.float32)
+    blob = R.pack_decoder_blob(params, R.DEC_S, device=cuda)
+    planes = R.pack_planes(code.to(cuda), R.DEC_S)
+    grid, bf = D.get_density(R.DEC_S, planes, (128, 128), blob, 1, density_thresh=0.1, density_step=2, jitters=[r.to(cuda) for r in rands],
+                             grid_dtype=torch.float32)
+    gr, gg = grid_ref.numpy(), grid.cpu().numpy()
+    rel = np.abs(gg - gr) / np.maximum(gr, 1e-3)
+    assert np.median(rel) < 2e-3 and rel.max() < 3e-2, (np.median(rel), rel.max())
+    diff = np.unpackbits(bf.cpu().numpy() ^ bf_ref, axis=-1).mean()
+    assert diff < 5e-3, diff
