@@ -260,12 +260,20 @@ def run_ours(args):
                 'd2h_bytes_per_step': int(out_host.numel() * 4)},
         'gpu_launches': gpu_launches,
         'clocks': clk,
-        'roofline': {'kernel': 'k_gemm_tc (tcgen05 implicit-GEMM conv / GEMM of the UNet), timed as the whole DDIM stage',
-                     'bound': 'tensor', 'achieved': tf_achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                     'frac': tf_achieved / pk['tf_sustained'], 'peak_source': f"{pk['src']} (sustained cuBLAS bf16)", 'traffic': None},
-        'roofline_render': {'kernel': 'k_render_p', 'bound': 'hbm', 'achieved': render_bytes / (rend_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'],
-                            'unit': 'GB/s', 'frac': render_bytes / (rend_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'peak_source': pk['src'],
-                            'note': 'algorithmic gather bytes; the 1.5 MB/scene planes are L2-resident, so this is an L2-side figure'},
+        # dominant kernel of the step = the fused renderer (k_render_p2, ~64 % of the step): algorithmic gather + output bytes per
+        # launch / launch duration against the measured HBM copy peak; `traffic` = DRAM bytes of the same kernel from
+        # the committed ncu capture scaled to this launch -- the planes (1.5 MB/scene) are L2-resident, so real DRAM traffic is ~ the
+        # 20 B/ray output and the binding unit is the SM (MUFU / issue), see profiles/r01_ncu_prof_render_P_MMA.txt
+        'roofline': {'kernel': 'k_render_p2 (fused march + gather + MLP + composite), one launch per step', 'bound': 'hbm',
+                     'achieved': render_bytes / (rend_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': render_bytes / (rend_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'peak_source': pk['src'] + ' (burst copy)',
+                     'algorithmic_bytes_per_launch': render_bytes, 'traffic': rays * 12.4 + 16 * 1.6e6,
+                     'traffic_note': 'ncu dram__bytes (read+write) of k_render_p2: 12.4 B/ray + plane/bitfield first touch; gather is served by L1/L2'},
+        'roofline_unet': {'kernel': 'k_gemm_tc (tcgen05 implicit-GEMM conv / GEMM) + glue, timed as the whole DDIM stage', 'bound': 'tensor',
+                          'achieved': tf_achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': tf_achieved / pk['tf_sustained'],
+                          'peak_source': f"{pk['src']} (sustained cuBLAS bf16)",
+                          'note': 'large convs alone run at 1.2-1.3 PFLOP/s (profiles/r01_gemm_conv_microbench.txt); GroupNorm/attention glue and '
+                                  'the 8x8/16x16 levels pull the stage average down'},
     }
     if args.cpu_baseline:
         line['cpu_baseline'] = cpu_reference_sample(quick=True)
