@@ -7,8 +7,8 @@ from ssdnerf_b200 import renderer as R
 from tests.common import spiral_poses
 dev = torch.device('cuda:0')
 variant = sys.argv[1]
-vid = {'P': R.DEC_P, 'P_TC': R.DEC_P_TC, 'P_MMA': R.DEC_P_MMA, 'S': R.DEC_S}[variant]
-C = 32 if variant == 'S' else 6
+vid = {'P': R.DEC_P, 'P_TC': R.DEC_P_TC, 'P_MMA': R.DEC_P_MMA, 'S': R.DEC_S, 'S_MMA': R.DEC_S_MMA, 'S_TC': R.DEC_S_TC}[variant]
+C = 32 if variant[0] == 'S' else 6
 B, V = 4, 8
 g = torch.Generator().manual_seed(0)
 code = torch.randn(B, 3, C, 128, 128, generator=g).clamp(-2, 2).to(dev)

@@ -299,7 +299,7 @@ int ssdnerf_density_update(int variant, const void* planes, uint32_t plane_h, ui
                            uint32_t num_scenes, uint32_t grid_size, float bound, const float* jitter, float decay,
                            void* density_grid, int grid_is_half, void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool is_s = variant == SSDNERF_DEC_S;
+    const bool is_s = variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC;
     if (!is_s && variant != SSDNERF_DEC_P && variant != SSDNERF_DEC_P_SIMT && variant != SSDNERF_DEC_P_TC && variant != SSDNERF_DEC_P_MMA)
         return set_error_msg(SSDNERF_ERR_ARG, "density_update: unknown decoder variant");
     if (!planes || !decoder_blob || !density_grid || !workspace) return set_error_msg(SSDNERF_ERR_ARG, "density_update: NULL argument");

@@ -263,14 +263,14 @@ extern "C" {
 
 size_t ssdnerf_decoder_blob_floats(int variant) {
     if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) return DecP::BLOB;
-    if (variant == SSDNERF_DEC_S) return ssdnerf::dec_s_blob_floats();
+    if (variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC) return ssdnerf::dec_s_blob_floats();
     return 0;
 }
 
 size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp) {
     const size_t texels = (size_t)B * 3 * Hp * Wp;
     if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) return texels * 8 * sizeof(float);
-    if (variant == SSDNERF_DEC_S) return texels * 32 * sizeof(__half);
+    if (variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC) return texels * 32 * sizeof(__half);
     return 0;
 }
 
@@ -283,7 +283,7 @@ int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, 
     if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) {
         if (C != 6) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: variant P expects 6 channels per plane");
         k_pack_planes<float, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(code, B, C, Hp, Wp, (float*)planes);
-    } else if (variant == SSDNERF_DEC_S) {
+    } else if (variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC) {
         if (C != 32) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: variant S expects 32 channels per plane");
         k_pack_planes<__half, 32><<<blocks, 256, 0, (cudaStream_t)stream>>>(code, B, C, Hp, Wp, (__half*)planes);
     } else {
@@ -378,7 +378,8 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
         }
         return 0;
     }
-    if (a->variant == SSDNERF_DEC_S) return ssdnerf::render_s_launch(p, a->emulate_schedule, hist, sms, stream);
+    if (a->variant == SSDNERF_DEC_S_MMA || a->variant == SSDNERF_DEC_S) return ssdnerf::render_s2_launch(p, a->emulate_schedule, hist, sms, stream);
+    if (a->variant == SSDNERF_DEC_S_TC) return ssdnerf::render_s_launch(p, a->emulate_schedule, hist, sms, stream);
     return set_error_msg(SSDNERF_ERR_ARG, "render_fwd: unknown decoder variant");
 }
 

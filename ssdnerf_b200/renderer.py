@@ -13,7 +13,9 @@ DEC_S = 1   # TriPlaneDecoder class defaults: base 96->128, density 128->1, colo
 DEC_P_SIMT = 2   # DEC_P on the CUDA cores (plain fp32)
 DEC_P_TC = 3     # DEC_P with a split-precision tcgen05 base layer
 DEC_P_MMA = 4    # DEC_P, warp-synchronous split-precision mma.sync base layer
-_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6, DEC_P_MMA: 6}
+DEC_S_MMA = 5    # DEC_S, warp-synchronous mma.sync kernel
+DEC_S_TC = 6     # DEC_S, CTA-synchronous tcgen05 kernel
+_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6, DEC_P_MMA: 6, DEC_S_MMA: 32, DEC_S_TC: 32}
 
 
 def detect_variant(params):
@@ -48,7 +50,7 @@ def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cu
                  p['dir_net.0.weight'].t().contiguous().reshape(-1), p['dir_net.0.bias'],      # [16][64]
                  p['color_net.0.weight'].reshape(-1), torch.cat([p['color_net.0.bias'], torch.zeros(1)]),
                  torch.tensor([sigmoid_saturation, 0, 0, 0])]
-    elif variant == DEC_S:
+    elif variant in (DEC_S, DEC_S_MMA, DEC_S_TC):
         w1 = _plane_major(p['base_net.0.weight'], 32)                             # [128][96] (N x K, K contiguous)
         wc0 = p['color_net.0.weight']                                             # [128][144]: cols 0..127 base_act, 128..143 SH
         parts = [w1.reshape(-1), p['base_net.0.bias'],

@@ -42,12 +42,12 @@ def _run_gpu(variant, vid, params, code, bf, poses, intr, res, cuda, max_steps, 
     return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
 
 
-@pytest.mark.parametrize('variant', ['P', 'P_SIMT', 'P_TC', 'S'])
+@pytest.mark.parametrize('variant', ['P', 'P_SIMT', 'P_TC', 'S', 'S_TC'])
 @pytest.mark.parametrize('grid', ['ones', 'sphere'])
 def test_config1_explicit_rays(cuda, variant, grid):
     """64x64 render, max_steps=32 (fixed step dt_max), bit-exact integer trace."""
     from ssdnerf_b200 import renderer as R
-    vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'S': R.DEC_S}[variant]
+    vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'S': R.DEC_S, 'S_TC': R.DEC_S_TC}[variant]
     code, poses, intr = config1(variant[0])
     params = rp.make_decoder_params(variant[0], 0)
     bf = _bitfields()[grid]
@@ -59,7 +59,7 @@ def test_config1_explicit_rays(cuda, variant, grid):
     out = _run_gpu(variant, vid, params, code, bf, poses, intr, res, cuda, max_steps, True, max(cap, 1))
     counts_ref = np.array([len(t) for t in ref['trace']], np.int32)
     counts = out['num_samples'][0]
-    if variant != 'S':
+    if variant[0] != 'S':
         assert np.array_equal(counts, counts_ref)
     else:   # early termination depends on sigma; fp16 MLP may stop one sample apart on a handful of rays
         assert (counts != counts_ref).mean() < 5e-3
@@ -67,7 +67,7 @@ def test_config1_explicit_rays(cuda, variant, grid):
     tr = out['trace'][0]
     for i in np.nonzero(same)[0]:
         assert list(tr[i, :counts[i]]) == ref['trace'][i], f'ray {i}'
-    tol = TOL_S if variant == 'S' else TOL_P
+    tol = TOL_S if variant[0] == 'S' else TOL_P
     np.testing.assert_allclose(out['image'][0][same], ref['image'][same], **tol)
     np.testing.assert_allclose(out['weights_sum'][0][same], ref['weights_sum'][same], **tol)
     np.testing.assert_allclose(out['depth'][0][same], ref['depth'][same], rtol=tol['rtol'], atol=tol['atol'] * 4)
