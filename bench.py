@@ -341,7 +341,7 @@ def run_reference(args):
     vals, trips, t_all = [], [], []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r = cpu_reference_sample(unet_evals=3, views=2)
+        r = cpu_reference_sample(unet_evals=8, views=8)
         if i >= args.warmup:
             vals.append(r['value']); trips.append(r['triplanes_per_sec']); t_all.append(time.perf_counter() - t0)
     v, tr = float(np.mean(vals)), float(np.mean(trips))

@@ -154,6 +154,57 @@ SSDNERF_API size_t ssdnerf_render_workspace_bytes(uint32_t num_scenes, uint32_t 
 SSDNERF_API int ssdnerf_render_fwd(const ssdnerf_render_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 2b. Fused differentiable renderer (train / guidance branch), variant P.
+ *    replaces: lib/models/decoders/base_volume_renderer.py:59-77 (march_rays_train -> point_decode ->
+ *              batch_composite_rays_train), lib/ops/raymarching/raymarching.py:200-395 and the autograd
+ *              graph of triplane_decoder.py:119-179 for the gradient w.r.t. the triplane code;
+ *              lib/models/autodecoders/base_nerf.py:276-296 (pixel MSE + RegLoss terms of BaseNeRF.loss).
+ *    forward : per ray K6 march (perturbed start t0 = near + clamp(near*dt_gamma) * noise), decode, K7
+ *              compositing; writes weights_sum / depth / image [B][N] (and the per-ray sample count).
+ *    backward: re-marches the same samples, applies K8 with the saved weights_sum / image and
+ *              accumulates d(loss)/d(planes) into grad_planes (channels-last, layout of ssdnerf_pack_planes,
+ *              caller zero-fills); ssdnerf_unpack_plane_grads converts to the [B][3][6][H][W] code layout.
+ *    The decoder weights receive no gradient (frozen decoder, diffusion_nerf.py:273).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ssdnerf_render_train_args {
+    int variant;               /* SSDNERF_DEC_P */
+    uint32_t num_scenes, rays_per_scene;
+    const float* rays_o;       /* [B][N][3] */
+    const float* rays_d;       /* [B][N][3] */
+    const float* noises;       /* [B][N] uniform [0,1) (perturb=True) or NULL */
+    const void* planes;        /* from ssdnerf_pack_planes(SSDNERF_DEC_P, ...) */
+    uint32_t plane_h, plane_w;
+    const uint8_t* bitfield;   /* [B][H^3/8] */
+    uint32_t grid_size;
+    const float* decoder_blob;
+    const float* dt_gamma;     /* [B] or NULL */
+    float bound, min_near, T_thresh;
+    uint32_t max_steps;
+    float* weights_sum;        /* [B][N]    forward: out, backward: in (saved) */
+    float* depth;              /* [B][N]    forward: out (optional) */
+    float* image;              /* [B][N][3] forward: out, backward: in (saved) */
+    int32_t* num_samples;      /* [B][N]    forward: out (optional) */
+    const float* grad_ws;      /* [B][N]    backward: in (optional) */
+    const float* grad_image;   /* [B][N][3] backward: in */
+    float* grad_planes;        /* [B][3][H][W][8] fp32, backward: accumulated into */
+    uint32_t* counter;         /* 4 bytes of device scratch (tile counter) */
+} ssdnerf_render_train_args;
+
+/* lib/core/utils/nerf_utils.py:17-61 get_cam_rays: poses [B][V][4][4] c2w, intrinsics [B][V][4] -> rays_o / rays_d [B][V][h][w][3] */
+SSDNERF_API int ssdnerf_cam_rays(const float* poses, const float* intrinsics, uint32_t B, uint32_t V, uint32_t h, uint32_t w,
+                     float* rays_o, float* rays_d, void* stream);
+SSDNERF_API int ssdnerf_render_train_fwd(const ssdnerf_render_train_args* args, void* stream);
+SSDNERF_API int ssdnerf_render_train_bwd(const ssdnerf_render_train_args* args, void* stream);
+/* grad_code[b][p][c][y][x] (=|+=) grad_planes[b][p][y][x][c] + reg_coef * code[...]   (code may be NULL) */
+SSDNERF_API int ssdnerf_unpack_plane_grads(const float* grad_planes, const float* code, float reg_coef, uint32_t B, uint32_t Hp, uint32_t Wp,
+                               int accumulate, float* grad_code, void* stream);
+/* out = image + bg * (1 - ws);  *loss += coef_loss * sum (out - target)^2;  grad_image = coef_grad * (out - target);
+ * grad_ws = -bg * sum_c grad_image.  (MSELoss 'mean' * weights are folded into the two coefficients by the caller.) */
+SSDNERF_API int ssdnerf_mse_render_loss(const float* image, const float* weights_sum, const float* target, uint64_t rays, float bg_color,
+                            float coef_loss, float coef_grad, float* out_rgb /* optional */, float* grad_image, float* grad_ws,
+                            float* loss /* [1], accumulated */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 3. Occupancy-grid builder.
  *    replaces: lib/models/autodecoders/base_nerf.py:318-389 (update_extra_state, full-update branch:
  *              jittered voxel centres -> morton3D -> point_density_decode -> EMA max -> mean -> packbits)

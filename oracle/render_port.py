@@ -89,7 +89,7 @@ def point_decode(params, xyzs, dirs, code_single, density_only=False, sigmoid_sa
     sig = torch.exp(F.linear(base_act, params['density_net.0.weight'], params['density_net.0.bias'])).squeeze(-1)
     if density_only:
         return sig, None
-    sh = torch.from_numpy(orc.sh_encode(dirs.numpy(), 4))
+    sh = torch.from_numpy(orc.sh_encode(dirs.numpy(), 4)).to(base_x.dtype)
     if 'dir_net.0.weight' in params:
         color_in = F.silu(base_x + F.linear(sh, params['dir_net.0.weight'], params['dir_net.0.bias']))
         rgb = torch.sigmoid(F.linear(color_in, params['color_net.0.weight'], params['color_net.0.bias']))

@@ -42,6 +42,22 @@ class RenderArgs(ctypes.Structure):
     ]
 
 
+class RenderTrainArgs(ctypes.Structure):
+    """mirror of `ssdnerf_render_train_args` (include/ssdnerf_b200.h)"""
+    _fields_ = [
+        ('variant', c_int), ('num_scenes', c_u32), ('rays_per_scene', c_u32),
+        ('rays_o', c_void_p), ('rays_d', c_void_p), ('noises', c_void_p),
+        ('planes', c_void_p), ('plane_h', c_u32), ('plane_w', c_u32),
+        ('bitfield', c_void_p), ('grid_size', c_u32),
+        ('decoder_blob', c_void_p), ('dt_gamma', c_void_p),
+        ('bound', c_f32), ('min_near', c_f32), ('T_thresh', c_f32),
+        ('max_steps', c_u32),
+        ('weights_sum', c_void_p), ('depth', c_void_p), ('image', c_void_p), ('num_samples', c_void_p),
+        ('grad_ws', c_void_p), ('grad_image', c_void_p), ('grad_planes', c_void_p),
+        ('counter', c_void_p),
+    ]
+
+
 def lib():
     """Load the native library; raises if it has not been built (python -m ssdnerf_b200.build)."""
     global _lib

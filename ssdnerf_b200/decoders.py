@@ -7,8 +7,10 @@ return_loss)` returning `dict(weights_sum, depth, image)` as per-scene lists in 
 `point_density_decode`, attributes `bound / min_near / max_steps / aabb`.
 
 eval mode (`self.training == False`): ONE fused launch sequence (csrc/render_fused.cu, csrc/render_tc.cu).
-train mode: the reference's op-by-op composition on the per-op kernels of this library (march_rays_train ->
-point_decode -> composite_rays_train with analytic backward) so autograd through the renderer keeps working.
+train mode: frozen decoder of the shipped-config shape (guidance / code optimisation, diffusion_nerf.py:273) ->
+fused differentiable renderer (csrc/render_train.cu, gradient w.r.t. the code only); otherwise the reference's
+op-by-op composition on the per-op kernels of this library (march_rays_train -> point_decode ->
+composite_rays_train with analytic backward) so autograd into the decoder weights keeps working.
 """
 import torch
 import torch.nn as nn
@@ -20,6 +22,29 @@ from .activation import TruncExp
 from .raymarching import batch_composite_rays_train, batch_near_far_from_aabb, march_rays_train
 from .registry import MODULES, build_module
 from .shencoder import SHEncoder
+
+
+class _FusedTrainRender(torch.autograd.Function):
+    """march + decode + composite as ONE differentiable op (gradient w.r.t. `code` [B,3,6,H,W] only)."""
+
+    @staticmethod
+    def forward(ctx, code, rays_o, rays_d, bitfield, blob, noises, dt_gamma, cfg):
+        planes = R.pack_planes(code, R.DEC_P)
+        hw = tuple(code.shape[-2:])
+        out = R.render_train_fwd(planes, hw, bitfield, blob, rays_o, rays_d, noises=noises, dt_gamma=dt_gamma, **cfg)
+        ctx.save_for_backward(planes, rays_o, rays_d, bitfield, blob, noises, dt_gamma, out['weights_sum'], out['image'])
+        ctx.hw, ctx.cfg = hw, cfg
+        ctx.mark_non_differentiable(out['depth'])      # the reference's K8 has no depth gradient either (raymarching.py:333-343)
+        return out['weights_sum'], out['depth'], out['image']
+
+    @staticmethod
+    def backward(ctx, grad_ws, grad_depth, grad_image):
+        planes, rays_o, rays_d, bitfield, blob, noises, dt_gamma, ws, image = ctx.saved_tensors
+        if grad_image is None:
+            grad_image = torch.zeros_like(image)
+        grad_code = R.render_train_bwd(planes, ctx.hw, bitfield, blob, rays_o, rays_d, ws, image, grad_ws, grad_image,
+                                       noises=noises, dt_gamma=dt_gamma, **ctx.cfg)
+        return grad_code, None, None, None, None, None, None, None
 
 
 class VolumeRenderer(nn.Module):
@@ -216,7 +241,46 @@ class TriPlaneDecoder(VolumeRenderer):
         # eval mode returns per-scene lists (base_volume_renderer.py:90-123)
         return dict(weights_sum=list(out['weights_sum']), depth=list(out['depth']), image=list(out['image']))
 
+    def _fused_train_ok(self, rays_o, code, grid_size):
+        if not getattr(self, 'fused_train', True):      # set False to force the per-op composition (A/B tests)
+            return False
+        if self.code_dropout is not None or any(p.requires_grad for p in self.parameters()):
+            return False
+        if not isinstance(rays_o, torch.Tensor) and len({r.size(0) for r in rays_o}) != 1:
+            return False
+        if not isinstance(grid_size, int) and len(set(grid_size)) != 1:
+            return False
+        try:
+            return self.fused_variant() == R.DEC_P and code.size(2) == 6
+        except N.SSDNeRFNativeError:
+            return False
+
+    def _forward_train_fused(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh):
+        if not isinstance(rays_o, torch.Tensor):
+            rays_o, rays_d = torch.stack(list(rays_o)), torch.stack(list(rays_d))
+        num_scenes = rays_o.size(0)
+        rays_o, rays_d = rays_o.reshape(num_scenes, -1, 3).contiguous().float(), rays_d.reshape(num_scenes, -1, 3).contiguous().float()
+        if not isinstance(grid_size, int):
+            grid_size = grid_size[0]
+        if isinstance(dt_gamma, (int, float)):
+            dtg = None if dt_gamma == 0 else torch.full((num_scenes,), float(dt_gamma), device=rays_o.device)
+        else:
+            dtg = torch.as_tensor(dt_gamma, dtype=torch.float32, device=rays_o.device).reshape(num_scenes).contiguous()
+        if isinstance(perturb, torch.Tensor):          # extension: inject the K6 start offsets (parity tests)
+            noises = perturb.reshape(num_scenes, -1).contiguous().float()
+        else:
+            noises = torch.rand(num_scenes, rays_o.size(1), device=rays_o.device) if perturb else None
+        if isinstance(density_bitfield, (list, tuple)):
+            density_bitfield = torch.stack(list(density_bitfield))
+        cfg = dict(grid_size=int(grid_size), bound=float(self.bound), min_near=float(self.min_near), max_steps=int(self.max_steps),
+                   T_thresh=float(T_thresh))
+        ws, depth, image = _FusedTrainRender.apply(code, rays_o, rays_d, density_bitfield.reshape(num_scenes, -1).contiguous(),
+                                                   self.packed_blob(), noises, dtg, cfg)
+        return dict(weights_sum=ws, depth=depth, image=image)
+
     def _forward_train(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh):
+        if self._fused_train_ok(rays_o, code, grid_size):
+            return self._forward_train_fused(rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh)
         num_scenes = len(rays_o)
         if isinstance(grid_size, int):
             grid_size = [grid_size] * num_scenes
@@ -225,8 +289,13 @@ class TriPlaneDecoder(VolumeRenderer):
         nears, fars = batch_near_far_from_aabb(rays_o, rays_d, self.aabb, self.min_near)
         xyzs, dirs, deltas, rays = [], [], [], []
         for ro, rd, bf, ne, fa, gs, dtg in zip(rays_o, rays_d, density_bitfield, nears, fars, grid_size, dt_gamma):
-            x, d, de, r = march_rays_train(ro, rd, self.bound, bf, 1, gs, ne, fa, perturb=perturb, align=128, force_all_rays=True,
-                                           dt_gamma=float(dtg), max_steps=self.max_steps)
+            noi = None
+            if isinstance(perturb, torch.Tensor):
+                noi, per = perturb.reshape(num_scenes, -1)[len(rays)], True
+            else:
+                per = bool(perturb)
+            x, d, de, r = march_rays_train(ro, rd, self.bound, bf, 1, gs, ne, fa, perturb=per, align=128, force_all_rays=True,
+                                           dt_gamma=float(dtg), max_steps=self.max_steps, noises=noi)
             xyzs.append(x); dirs.append(d); deltas.append(de); rays.append(r)
         sigmas, rgbs, num_points = self.point_decode(xyzs, dirs, code)
         weights_sum, depth, image = batch_composite_rays_train(sigmas, rgbs, deltas, rays, num_points, T_thresh)

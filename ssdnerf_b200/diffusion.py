@@ -88,12 +88,19 @@ class GaussianDiffusion(nn.Module):
     # ------------------------------------------------------------------ single-step API
     @torch.no_grad()
     def pred_x_0(self, x_t, t, grad_guide_fn=None, concat_cond=None, cfg=dict(), update_denoising_output=False):
-        """gaussian_diffusion.py:180-240 without guidance."""
-        if grad_guide_fn is not None:
-            raise NotImplementedError('guided sampling (grad_guide_fn) needs the renderer backward; planned next (SURVEY.md §8 f1)')
+        """gaussian_diffusion.py:180-240.  Guidance differentiates `grad_guide_fn` w.r.t. x_0 (`grad_through_unet=False`
+        branch, :218-222); the reference's default of back-propagating through the denoiser needs a UNet backward
+         and raises."""
         clip_denoised = cfg.get('clip_denoised', True)
         clip_range = cfg.get('clip_range', [-1, 1])
+        guidance_gain = cfg.get('guidance_gain', 1.0)
+        snr_weight_power = cfg.get('snr_weight_power', 0.5)
+        if grad_guide_fn is not None and cfg.get('grad_through_unet', True):
+            raise NotImplementedError('guidance with grad_through_unet=True needs the hand-written UNet backward (SURVEY.md §8 f1); '
+                                      'set test_cfg.grad_through_unet=False to differentiate w.r.t. x_0 on the fused renderer')
         num_batches = x_t.size(0)
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(t, device=x_t.device)
         if t.dim() == 0 or len(t) != num_batches:
             t = t.expand(num_batches)
         sa = x_t.new_tensor(self.sqrt_alphas_bar)[t].reshape(-1, 1, 1, 1)
@@ -108,9 +115,75 @@ class GaussianDiffusion(nn.Module):
             x_0 = sa * x_t - s1 * out
         else:
             raise AttributeError(f'Unknown denoising mean output type [{self.denoising_mean_mode}].')
+        if grad_guide_fn is not None:
+            if clip_denoised:
+                x_0 = x_0.clamp(*clip_range)
+            with torch.enable_grad():
+                x_0 = x_0.detach().requires_grad_(True)
+                loss = grad_guide_fn(x_0)
+                grad = torch.autograd.grad(loss, x_0)[0]
+            x_0 = x_0.detach() - grad * ((s1 ** (2 - snr_weight_power * 2)) * (sa ** (snr_weight_power * 2 - 1)) * guidance_gain)
         if clip_denoised:
             x_0 = x_0.clamp(*clip_range)
+        if update_denoising_output and grad_guide_fn is not None:
+            if mode == 'EPS':
+                out = (x_t - x_0 * sa) / s1
+            elif mode == 'START_X':
+                out = x_0
+            else:
+                out = (sa * x_t - x_0) / s1
         return x_0, out
+
+    @torch.no_grad()
+    def p_sample_langevin(self, x_t, t, noise=None, cfg=dict(), grad_guide_fn=None, **kwargs):
+        """gaussian_diffusion.py:242-262"""
+        t = int(t)
+        langevin_delta = cfg.get('langevin_delta', 0.1)
+        sigma = float(self.sqrt_one_minus_alphas_bar[t])
+        x_0_pred, _ = self.pred_x_0(x_t, torch.as_tensor(t, device=x_t.device), grad_guide_fn=grad_guide_fn, cfg=cfg, **kwargs)
+        eps_t_pred = (x_t - float(self.sqrt_alphas_bar[t]) * x_0_pred) / sigma
+        if noise is None:
+            noise = torch.randn_like(x_t)
+        return x_t - 0.5 * langevin_delta * sigma * eps_t_pred + float(np.sqrt(langevin_delta)) * sigma * noise
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x_t, t, t_prev, noise=None, cfg=dict(), grad_guide_fn=None, **kwargs):
+        """gaussian_diffusion.py:264-293"""
+        t, t_prev = int(t), int(t_prev)
+        eta = cfg.get('eta', 0)
+        alpha_bar_t_prev = self.alphas_bar[t_prev] if t_prev >= 0 else self.alphas_bar_prev[0]
+        tilde_beta_t = self.tilde_betas_t[t]
+        x_0_pred, _ = self.pred_x_0(x_t, torch.as_tensor(t, device=x_t.device), grad_guide_fn=grad_guide_fn, cfg=cfg, **kwargs)
+        eps_t_pred = (x_t - float(self.sqrt_alphas_bar[t]) * x_0_pred) / float(self.sqrt_one_minus_alphas_bar[t])
+        x_prev = float(np.sqrt(alpha_bar_t_prev)) * x_0_pred + float(np.sqrt(1 - alpha_bar_t_prev - tilde_beta_t * (eta ** 2))) * eps_t_pred
+        if eta > 0:
+            if noise is None:
+                noise = torch.randn_like(x_t)
+            x_prev = x_prev + eta * float(np.sqrt(tilde_beta_t)) * noise
+        return x_prev, x_0_pred
+
+    @torch.no_grad()
+    def _ddim_sample_stepwise(self, noise, concat_cond=None, save_intermediates=False, grad_guide_fn=None, **kwargs):
+        """gaussian_diffusion.py:295-331 step by step (host timesteps: no device->host sync): guidance, langevin
+        correction steps, eta > 0 and `save_intermediates`.  The unguided eta=0 loop uses the captured graph instead."""
+        if concat_cond is not None:
+            raise NotImplementedError('concat_cond (image-conditioned denoiser) is not used by the shipped configs')
+        cfg = self.test_cfg
+        x_t = noise.detach().float()
+        num_timesteps = cfg.get('num_timesteps', self.num_timesteps)
+        langevin_steps = cfg.get('langevin_steps', 0)
+        langevin_t_range = cfg.get('langevin_t_range', [0, 1000])
+        timesteps = [int(t) for t in self.ddim_timesteps(num_timesteps)]
+        out = [] if save_intermediates else None
+        for step, t in enumerate(timesteps):
+            t_prev = timesteps[step + 1] if step + 1 < len(timesteps) else -1
+            x_t, x_0_pred = self.p_sample_ddim(x_t, t, t_prev, cfg=cfg, grad_guide_fn=grad_guide_fn, **kwargs)
+            if langevin_steps > 0 and langevin_t_range[0] < t_prev < langevin_t_range[1]:
+                for _ in range(langevin_steps):
+                    x_t = self.p_sample_langevin(x_t, t_prev, cfg=cfg, grad_guide_fn=grad_guide_fn, **kwargs)
+            if out is not None:
+                out.extend([x_0_pred, x_t])
+        return out if save_intermediates else x_t
 
     def ddim_timesteps(self, num_timesteps):
         """gaussian_diffusion.py:302-304, kept on the HOST (the reference moves them to the GPU and syncs per step)"""
@@ -130,17 +203,15 @@ class GaussianDiffusion(nn.Module):
     # ------------------------------------------------------------------ the loop
     @torch.no_grad()
     def ddim_sample(self, noise, show_pbar=False, concat_cond=None, save_intermediates=False, use_graph=True, **kwargs):
-        """gaussian_diffusion.py:295-331 (V-parameterisation, eta = 0, no guidance / langevin / concat_cond)."""
-        if kwargs.get('grad_guide_fn') is not None or self.test_cfg.get('langevin_steps', 0) > 0:
-            raise NotImplementedError('guided / langevin sampling needs the renderer backward; planned next (SURVEY.md §8 f1)')
-        if concat_cond is not None or save_intermediates:
-            raise NotImplementedError('concat_cond / save_intermediates are not part of the accelerated path yet')
-        if self.denoising_mean_mode.upper() != 'V':
-            raise NotImplementedError('the fused DDIM update implements the V-parameterisation every reference config uses')
+        """gaussian_diffusion.py:295-331.  Unguided eta=0 V-parameterisation (every unconditional config) = captured graph;
+        guidance / langevin / eta > 0 / save_intermediates = the step-wise loop on the same engine."""
         cfg = self.test_cfg
         eta = cfg.get('eta', 0)
-        if eta != 0:
-            raise NotImplementedError('eta > 0 (stochastic DDIM) is not part of the accelerated path')
+        if (kwargs.get('grad_guide_fn') is not None or cfg.get('langevin_steps', 0) > 0 or save_intermediates or eta != 0
+                or self.denoising_mean_mode.upper() != 'V'):
+            return self._ddim_sample_stepwise(noise, concat_cond=concat_cond, save_intermediates=save_intermediates, **kwargs)
+        if concat_cond is not None:
+            raise NotImplementedError('concat_cond (image-conditioned denoiser) is not used by the shipped configs')
         N.require_cuda(noise)
         num_steps = cfg.get('num_timesteps', self.num_timesteps)
         clip = bool(cfg.get('clip_denoised', True))

@@ -132,3 +132,104 @@ def render_fwd(variant, planes, plane_hw, bitfield, blob, rays_o=None, rays_d=No
     import ctypes
     N.check(N.lib().ssdnerf_render_fwd(ctypes.byref(a), N.stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused differentiable renderer (C ABI section 2b): train / guidance branch, gradient w.r.t. the triplane code
+# ---------------------------------------------------------------------------------------------------------------------
+def _train_args(planes, plane_hw, bitfield, blob, rays_o, rays_d, noises, dt_gamma, grid_size, bound, min_near, max_steps, T_thresh):
+    B, n = rays_o.shape[0], rays_o.shape[1]
+    a = N.RenderTrainArgs()
+    a.variant = DEC_P
+    a.num_scenes, a.rays_per_scene = B, n
+    a.rays_o, a.rays_d, a.noises = N.ptr(rays_o), N.ptr(rays_d), N.ptr(noises)
+    a.planes, a.plane_h, a.plane_w = N.ptr(planes), plane_hw[0], plane_hw[1]
+    a.bitfield, a.grid_size = N.ptr(bitfield), grid_size
+    a.decoder_blob, a.dt_gamma = N.ptr(blob), N.ptr(dt_gamma)
+    a.bound, a.min_near, a.T_thresh, a.max_steps = bound, min_near, T_thresh, max_steps
+    return a
+
+
+def render_train_fwd(planes, plane_hw, bitfield, blob, rays_o, rays_d, noises=None, dt_gamma=None, grid_size=64, bound=1.0,
+                     min_near=0.2, max_steps=256, T_thresh=1e-4, want_counts=False):
+    """Train-branch forward (K6 march + decode + K7 compositing fused). rays [B,N,3]; noises [B,N] in [0,1) or None.
+    Returns dict(weights_sum [B,N], depth [B,N], image [B,N,3], num_samples [B,N] | None)."""
+    import ctypes
+    N.require_cuda(planes, bitfield, blob, rays_o, rays_d)
+    dev = planes.device
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    bitfield = bitfield.contiguous()
+    noises = None if noises is None else noises.contiguous().float()
+    dt_gamma = None if dt_gamma is None else dt_gamma.contiguous().float().to(dev)
+    B, n = rays_o.shape[0], rays_o.shape[1]
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(weights_sum=torch.empty(B, n, **f32), depth=torch.empty(B, n, **f32), image=torch.empty(B, n, 3, **f32),
+               num_samples=torch.empty(B, n, dtype=torch.int32, device=dev) if want_counts else None)
+    counter = torch.empty(1, dtype=torch.int32, device=dev)
+    a = _train_args(planes, plane_hw, bitfield, blob, rays_o, rays_d, noises, dt_gamma, grid_size, bound, min_near, max_steps, T_thresh)
+    a.weights_sum, a.depth, a.image, a.num_samples = N.ptr(out['weights_sum']), N.ptr(out['depth']), N.ptr(out['image']), N.ptr(out['num_samples'])
+    a.counter = N.ptr(counter)
+    N.check(N.lib().ssdnerf_render_train_fwd(ctypes.byref(a), N.stream_ptr()))
+    return out
+
+
+def render_train_bwd(planes, plane_hw, bitfield, blob, rays_o, rays_d, weights_sum, image, grad_ws, grad_image, noises=None,
+                     dt_gamma=None, grid_size=64, bound=1.0, min_near=0.2, max_steps=256, T_thresh=1e-4, code=None, reg_coef=0.0):
+    """Train-branch backward: d(loss)/d(code) [B,3,6,H,W] from d(loss)/d(image) [B,N,3] and d(loss)/d(weights_sum) [B,N]
+    (+ reg_coef * code when `code` is given: the RegLoss(power=2) gradient of BaseNeRF.loss)."""
+    import ctypes
+    N.require_cuda(planes, bitfield, blob, rays_o, rays_d, weights_sum, image, grad_image)
+    dev = planes.device
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    bitfield = bitfield.contiguous()
+    noises = None if noises is None else noises.contiguous().float()
+    dt_gamma = None if dt_gamma is None else dt_gamma.contiguous().float().to(dev)
+    weights_sum, image = weights_sum.contiguous().float(), image.contiguous().float()
+    grad_image = grad_image.contiguous().float()
+    grad_ws = None if grad_ws is None else grad_ws.contiguous().float()
+    B = rays_o.shape[0]
+    H, W = plane_hw
+    gplanes = torch.zeros(B, 3, H, W, 8, dtype=torch.float32, device=dev)
+    counter = torch.empty(1, dtype=torch.int32, device=dev)
+    a = _train_args(planes, plane_hw, bitfield, blob, rays_o, rays_d, noises, dt_gamma, grid_size, bound, min_near, max_steps, T_thresh)
+    a.weights_sum, a.image = N.ptr(weights_sum), N.ptr(image)
+    a.grad_ws, a.grad_image, a.grad_planes = N.ptr(grad_ws), N.ptr(grad_image), N.ptr(gplanes)
+    a.counter = N.ptr(counter)
+    N.check(N.lib().ssdnerf_render_train_bwd(ctypes.byref(a), N.stream_ptr()))
+    grad_code = torch.empty(B, 3, 6, H, W, dtype=torch.float32, device=dev)
+    if code is not None:
+        code = code.contiguous().float()
+    N.check(N.lib().ssdnerf_unpack_plane_grads(N.ptr(gplanes), N.ptr(code), N.c_f32(reg_coef), N.c_u32(B), N.c_u32(H), N.c_u32(W),
+                                               N.c_int(0), N.ptr(grad_code), N.stream_ptr()))
+    return grad_code
+
+
+def mse_render_loss(image, weights_sum, target, bg_color, coef_loss, coef_grad, want_rgb=False):
+    """Pixel term of BaseNeRF.loss (base_nerf.py:283-287) fused with its gradient.
+    Returns (loss [1] = coef_loss * sum((image + bg (1 - ws) - target)^2), grad_image, grad_ws, out_rgb | None)."""
+    N.require_cuda(image, weights_sum, target)
+    image, weights_sum, target = image.contiguous().float(), weights_sum.contiguous().float(), target.contiguous().float()
+    rays = weights_sum.numel()
+    loss = torch.zeros(1, dtype=torch.float32, device=image.device)
+    g_image, g_ws = torch.empty_like(image), torch.empty_like(weights_sum)
+    out_rgb = torch.empty_like(image) if want_rgb else None
+    N.check(N.lib().ssdnerf_mse_render_loss(N.ptr(image), N.ptr(weights_sum), N.ptr(target), N.ctypes.c_uint64(rays), N.c_f32(bg_color),
+                                            N.c_f32(coef_loss), N.c_f32(coef_grad), N.ptr(out_rgb), N.ptr(g_image), N.ptr(g_ws),
+                                            N.ptr(loss), N.stream_ptr()))
+    return loss, g_image, g_ws, out_rgb
+
+
+def get_cam_rays(c2w, intrinsics, h, w):
+    """lib/core/utils/nerf_utils.py:57-61 (+ :17-54): pixel-centre pinhole rays, -> rays_o, rays_d [B,V,h,w,3].
+    Same arithmetic as the in-kernel ray generation of the fused eval renderer (csrc/render_common.cuh make_ray)."""
+    N.require_cuda(c2w, intrinsics)
+    B, V = c2w.shape[0], c2w.shape[1]
+    poses = c2w.float()
+    if poses.shape[-2] == 3:
+        poses = torch.cat([poses, poses.new_tensor([0, 0, 0, 1]).expand(B, V, 1, 4)], dim=-2)
+    poses, intrinsics = poses.contiguous(), intrinsics.contiguous().float()
+    rays_o = torch.empty(B, V, h, w, 3, dtype=torch.float32, device=c2w.device)
+    rays_d = torch.empty_like(rays_o)
+    N.check(N.lib().ssdnerf_cam_rays(N.ptr(poses), N.ptr(intrinsics), N.c_u32(B), N.c_u32(V), N.c_u32(h), N.c_u32(w),
+                                     N.ptr(rays_o), N.ptr(rays_d), N.stream_ptr()))
+    return rays_o, rays_d

@@ -124,3 +124,76 @@ def test_golden_unet_and_ddim_tables():
         return (sa * x_t - x0) / s1
     out = up.ddim_sample(oracle_v, torch.randn(1, 18, 8, 8, generator=torch.Generator().manual_seed(1)), dv, num_timesteps=50)
     np.testing.assert_allclose(out.numpy(), x0.numpy(), atol=2e-4)
+
+
+# ----------------------------------------------------------------------------- differentiable (train / guidance) branch
+def _train_case(n_rays=48, res=12, seed=3):
+    from oracle import train_port as tp
+    code, poses, intr = config1('P', seed=seed, res=res)
+    ro, rd = rp.get_cam_rays(poses[0], intr[0], res, res)
+    sel = np.linspace(0, res * res - 1, n_rays).astype(np.int64)       # spread over the image so most rays hit the sphere
+    ro, rd = ro.reshape(-1, 3).numpy()[sel], rd.reshape(-1, 3).numpy()[sel]
+    params = rp.make_decoder_params('P', seed=seed)
+    bf = rp.sphere_bitfield()
+    rng = np.random.default_rng(seed)
+    return tp, code[0] * 0.5, ro, rd, params, bf, rng.random(ro.shape[0]).astype(np.float32)
+
+
+def test_train_autograd_equals_k8_analytic_backward():
+    """torch autograd through the restated K7 forward == the C restatement of K8 (raymarching.cu:606-687) on the same samples,
+    including K8's rule that the sample at which T drops below T_thresh gets no gradient."""
+    tp, code, ro, rd, params, bf, noises = _train_case()
+    T_thresh = 0.3                                   # high threshold so many rays actually break early
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = orc.near_far_from_aabb(ro, rd, aabb, 0.2)
+    xyzs, dirs, deltas, rays = orc.march_rays_train(ro, rd, 1.0, bf, 1, 64, nears, fars, max_steps=256, noises=noises)
+    m = int(rays[:, 2].sum())
+    sig, rgb = rp.point_decode(params, torch.from_numpy(xyzs[:m]), torch.from_numpy(dirs[:m]), code)
+    sig = (sig * 6).detach().numpy().astype(np.float32); rgb = rgb.detach().numpy().astype(np.float32)
+    ws, depth, img = orc.composite_rays_train_forward(sig, rgb, deltas[:m], rays, T_thresh)
+    rng = np.random.default_rng(0)
+    g_ws, g_img = rng.standard_normal(ws.shape).astype(np.float32), rng.standard_normal(img.shape).astype(np.float32)
+    gs, gc = orc.composite_rays_train_backward(g_ws, g_img, sig, rgb, deltas[:m], rays, ws, img, T_thresh)
+    # the same composite in torch (float64) with the crossing-sample detach
+    st = torch.from_numpy(sig).double().requires_grad_(True); ct = torch.from_numpy(rgb).double().requires_grad_(True)
+    tot = 0
+    n_broke = 0
+    for r in range(rays.shape[0]):
+        off, cnt = int(rays[r, 1]), int(rays[r, 2])
+        T = torch.ones((), dtype=torch.float64); w_sum = 0; im = 0
+        for s in range(cnt):
+            k = off + s
+            crossing = float((T * torch.exp(-st[k] * float(deltas[k, 0]))).detach()) < T_thresh
+            sk, ck = (st[k].detach(), ct[k].detach()) if crossing else (st[k], ct[k])
+            a = 1 - torch.exp(-sk * float(deltas[k, 0]))
+            w = a * T
+            w_sum = w_sum + w; im = im + w * ck
+            T = T * (1 - a)
+            if crossing:
+                n_broke += 1
+                break
+        tot = tot + w_sum * float(g_ws[r]) + (im * torch.from_numpy(g_img[r]).double()).sum() if cnt else tot
+    g_s, g_c = torch.autograd.grad(tot, [st, ct])
+    assert n_broke > 5
+    np.testing.assert_allclose(g_s.numpy(), gs, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(g_c.numpy(), gc, rtol=2e-4, atol=2e-5)
+
+
+def test_train_render_gradient_finite_differences():
+    """d loss / d code of the restated loss chain vs central differences (float64)"""
+    tp, code, ro, rd, params, bf, noises = _train_case(n_rays=24)
+    rng = np.random.default_rng(1)
+    target = rng.random((1, ro.shape[0], 3)).astype(np.float32)
+    kw = dict(noises=noises[None], bg_color=1.0, pixel_weight=20.0, loss_coef=0.1 / 144, scale_num_ray=ro.shape[0], reg_weight=3e-3)
+    code = code[None].double()
+    loss, grad, out = tp.render_loss_grad(params, code, ro[None], rd[None], target, [bf], **kw)
+    assert float(loss) > 0 and float(grad.abs().max()) > 0
+    flat = grad.reshape(-1)
+    idx = torch.argsort(flat.abs(), descending=True)[:6]
+    eps = 1e-5
+    for i in idx.tolist():
+        d = torch.zeros_like(code).reshape(-1); d[i] = eps; d = d.reshape(code.shape)
+        lp, _ = tp.render_loss(params, code + d, ro[None], rd[None], target, [bf], **kw)
+        lm, _ = tp.render_loss(params, code - d, ro[None], rd[None], target, [bf], **kw)
+        fd = float(lp - lm) / (2 * eps)
+        assert abs(fd - float(flat[i])) <= 1e-5 * max(1.0, abs(fd)) + 2e-3 * abs(fd), (i, fd, float(flat[i]))

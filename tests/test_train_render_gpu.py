@@ -1,0 +1,233 @@
+"""Fused differentiable renderer (C-ABI section 2b) and the guidance path built on it.
+
+Forward (weights_sum / depth / image): vs the CPU oracle (rtol 2e-4 / atol 2e-5, fp32 MLP with fast intrinsics) and vs this
+library's per-op composition (march_rays_train -> point_decode -> composite_rays_train), whose kernels are bit-exact with the
+reference's own (tests/test_ref_gpu.py).  Per-ray sample counts are integers: exact.
+Backward (d loss / d code): vs float64 autograd of the oracle chain, relative L2 <= 1e-3; vs per-op autograd relative L2 <= 1e-4
+(both scatter with fp32 atomics, so not bit-identical)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_port as rp
+from oracle import train_port as tp
+from oracle import unet_port as up
+from tests.common import config1, spiral_poses
+
+pytestmark = pytest.mark.gpu
+
+TOL_P = dict(rtol=2e-4, atol=2e-5)
+
+
+def _rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _case(B=2, n_rays=512, seed=5, res=32, density_bias=1.5):
+    g = torch.Generator().manual_seed(seed)
+    code = (torch.randn(B, 3, 6, 128, 128, generator=g) * 0.7).clamp(-2, 2)
+    poses = torch.from_numpy(spiral_poses(B))
+    f = 131.25 * res / 128
+    intr = torch.tensor([f, f, res / 2, res / 2]).expand(B, 4)
+    ros, rds = [], []
+    for b in range(B):
+        ro, rd = rp.get_cam_rays(poses[b], intr[b], res, res)
+        sel = torch.randperm(res * res, generator=g)[:n_rays]
+        ros.append(ro.reshape(-1, 3)[sel]); rds.append(rd.reshape(-1, 3)[sel])
+    rays_o, rays_d = torch.stack(ros), torch.stack(rds)
+    params = rp.make_decoder_params('P', seed)
+    params['density_net.0.bias'] = params['density_net.0.bias'] + density_bias      # opaque enough for early termination
+    bf = np.stack([rp.sphere_bitfield(radius=0.6), rp.sphere_bitfield(radius=0.45)][:B])
+    noises = torch.rand(B, n_rays, generator=g)
+    dt_gamma = torch.tensor([0.0, 0.004][:B])
+    target = torch.rand(B, n_rays, 3, generator=g)
+    return code, rays_o, rays_d, params, bf, noises, dt_gamma, target
+
+
+def _decoder(params, cuda, frozen=True):
+    import ssdnerf_b200 as S
+    dec = S.build_module(dict(type='TriPlaneDecoder', base_layers=[18, 64], density_layers=[64, 1], color_layers=[64, 3],
+                              use_dir_enc=True, dir_layers=[16, 64], max_steps=256))
+    sd = dec.state_dict(); sd.update(params); dec.load_state_dict(sd)
+    dec = dec.to(cuda).train()
+    dec.requires_grad_(not frozen)
+    return dec
+
+
+def test_cam_rays_match_oracle(cuda):
+    from ssdnerf_b200 import renderer as R
+    poses = torch.from_numpy(spiral_poses(3))[None]
+    intr = torch.tensor([[[40.0, 41.0, 15.5, 16.25]]]).expand(1, 3, 4).contiguous()
+    ro, rd = R.get_cam_rays(poses.to(cuda), intr.to(cuda), 24, 32)
+    ro_ref, rd_ref = rp.get_cam_rays(poses, intr, 24, 32)
+    assert torch.equal(ro.cpu(), ro_ref)
+    np.testing.assert_allclose(rd.cpu().numpy(), rd_ref.numpy(), rtol=1e-6, atol=1e-7)      # <= 1 ulp (torch matmul order)
+
+
+@pytest.mark.parametrize('T_thresh', [1e-4, 0.2])
+def test_train_forward_vs_oracle_and_per_op(cuda, T_thresh):
+    from ssdnerf_b200 import renderer as R
+    code, rays_o, rays_d, params, bf, noises, dt_gamma, _ = _case()
+    B = code.shape[0]
+    blob = R.pack_decoder_blob(params, R.DEC_P, device=cuda)
+    planes = R.pack_planes(code.to(cuda), R.DEC_P)
+    bft = torch.from_numpy(bf).to(cuda)
+    out = R.render_train_fwd(planes, (128, 128), bft, blob, rays_o.to(cuda), rays_d.to(cuda), noises=noises.to(cuda),
+                             dt_gamma=dt_gamma.to(cuda), T_thresh=T_thresh, want_counts=True)
+    n_break = 0
+    for b in range(B):
+        ws, depth, img = tp.render_train_scene(params, code[b], rays_o[b].numpy(), rays_d[b].numpy(), bf[b], noises[b].numpy(),
+                                               dt_gamma=float(dt_gamma[b]), T_thresh=T_thresh, dtype=torch.float32)
+        np.testing.assert_allclose(out['weights_sum'][b].cpu().numpy(), ws.numpy(), **TOL_P)
+        np.testing.assert_allclose(out['image'][b].cpu().numpy(), img.numpy(), **TOL_P)
+        np.testing.assert_allclose(out['depth'][b].cpu().numpy(), depth.numpy(), rtol=2e-4, atol=1e-4)
+        n_break += int((ws > 1 - T_thresh).sum())
+    assert n_break > 20                                                  # the early-termination branch is exercised
+    # per-op composition of this library (same march kernel as the reference, torch decode)
+    dec = _decoder(params, cuda)
+    dec.fused_train = False
+    with torch.no_grad():
+        ref = dec(rays_o.to(cuda), rays_d.to(cuda), code.to(cuda), bft, 64, dt_gamma=dt_gamma.tolist(), perturb=noises.to(cuda), T_thresh=T_thresh)
+    for k in ('weights_sum', 'image'):
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].cpu().numpy(), **TOL_P)
+    np.testing.assert_allclose(out['depth'].cpu().numpy(), ref['depth'].cpu().numpy(), rtol=2e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('T_thresh', [1e-4, 0.2])
+def test_train_backward_vs_oracle_and_per_op(cuda, T_thresh):
+    code, rays_o, rays_d, params, bf, noises, dt_gamma, target = _case(n_rays=256)
+    B, n = rays_o.shape[:2]
+    g = torch.Generator().manual_seed(1)
+    g_img, g_ws = torch.randn(B, n, 3, generator=g), torch.randn(B, n, generator=g)
+    # oracle: float64 autograd of sum(image * g_img + ws * g_ws)
+    cref = code.clone().double().requires_grad_(True)
+    tot = 0
+    for b in range(B):
+        ws, _, img = tp.render_train_scene(params, cref[b], rays_o[b].numpy(), rays_d[b].numpy(), bf[b], noises[b].numpy(),
+                                           dt_gamma=float(dt_gamma[b]), T_thresh=T_thresh)
+        tot = tot + (img * g_img[b].double()).sum() + (ws * g_ws[b].double()).sum()
+    grad_ref, = torch.autograd.grad(tot, cref)
+    bft = torch.from_numpy(bf).to(cuda)
+    grads = {}
+    for fused in (True, False):
+        dec = _decoder(params, cuda)
+        dec.fused_train = fused
+        c = code.to(cuda).requires_grad_(True)
+        out = dec(rays_o.to(cuda), rays_d.to(cuda), c, bft, 64, dt_gamma=dt_gamma.tolist(), perturb=noises.to(cuda), T_thresh=T_thresh)
+        loss = (out['image'] * g_img.to(cuda)).sum() + (out['weights_sum'] * g_ws.to(cuda)).sum()
+        grads[fused], = torch.autograd.grad(loss, c)
+    assert float(grad_ref.abs().max()) > 0
+    assert _rel_l2(grads[True], grad_ref) < 1e-3, _rel_l2(grads[True], grad_ref)
+    assert _rel_l2(grads[True], grads[False]) < 1e-4, _rel_l2(grads[True], grads[False])
+    # untouched texels stay exactly zero
+    assert bool(((grads[True] == 0) == (grads[False] == 0)).float().mean() > 0.999)
+
+
+def _model(cuda, params, test_cfg, unet_sd=None, spec=None):
+    import ssdnerf_b200 as S
+    unet_cfg = dict(type='DenoisingUnetMod', image_size=128, in_channels=18, base_channels=64, channels_cfg=[1, 2],
+                    resblocks_per_downsample=1, dropout=0.0, use_scale_shift_norm=True, num_heads=2, attention_res=[])
+    model = S.build_model(dict(
+        type='DiffusionNeRF', code_size=(3, 6, 128, 128), code_reshape=(18, 128, 128), grid_size=64, bg_color=1,
+        decoder_use_ema=False, diffusion_use_ema=False, freeze_decoder=True,
+        pixel_loss=dict(type='MSELoss', loss_weight=20.0), reg_loss=dict(type='RegLoss', power=2, loss_weight=3e-3),
+        diffusion=dict(type='GaussianDiffusion', num_timesteps=1000, betas_cfg=dict(type='linear'), denoising=unet_cfg),
+        decoder=dict(type='TriPlaneDecoder', base_layers=[18, 64], density_layers=[64, 1], color_layers=[64, 3], use_dir_enc=True,
+                     dir_layers=[16, 64], max_steps=256)), test_cfg=test_cfg)
+    dsd = model.decoder.state_dict(); dsd.update(params); model.decoder.load_state_dict(dsd)
+    if unet_sd is not None:
+        model.diffusion.denoising.load_state_dict(unet_sd)
+    return model.to(cuda).eval()
+
+
+def test_loss_fused_vs_oracle_and_module_composition(cuda):
+    """BaseNeRF.loss: fused (render + blend + MSE + RegLoss as one op) == oracle == reference-style module composition"""
+    code, rays_o, rays_d, params, bf, noises, dt_gamma, target = _case(n_rays=256)
+    B, n = rays_o.shape[:2]
+    cfg = dict(loss_coef=0.1 / (128 * 128))
+    model = _model(cuda, params, cfg)
+    dec = model.decoder.train()
+    bft = torch.from_numpy(bf).to(cuda)
+    res = {}
+    for fused in (True, False):
+        dec.fused_train = fused
+        c = code.to(cuda).requires_grad_(True)
+        rgb, loss, ld = model.loss(dec, c, bft, target.to(cuda), rays_o.to(cuda), rays_d.to(cuda), dt_gamma.to(cuda) if fused else dt_gamma.tolist(),
+                                   scale_num_ray=n, cfg=cfg, perturb=noises.to(cuda))
+        grad, = torch.autograd.grad(loss * B, c)
+        res[fused] = (float(loss), grad, rgb.detach(), {k: float(v) for k, v in ld.items()})
+    loss_ref, grad_ref, rgb_ref = tp.render_loss_grad(params, code, rays_o.numpy(), rays_d.numpy(), target.numpy(), bf, noises=noises.numpy(),
+                                                      dt_gamma=dt_gamma.numpy(), bg_color=1.0, pixel_weight=20.0, loss_coef=cfg['loss_coef'],
+                                                      scale_num_ray=n, reg_weight=3e-3)
+    assert set(res[True][3]) == {'pixel_loss', 'reg_loss'}
+    assert abs(res[True][0] - float(loss_ref)) <= 2e-4 * abs(float(loss_ref))
+    assert abs(res[True][0] - res[False][0]) <= 2e-5 * abs(res[False][0])
+    np.testing.assert_allclose(res[True][2].cpu().numpy(), rgb_ref.numpy(), **TOL_P)
+    assert _rel_l2(res[True][1], grad_ref * B) < 1e-3
+    assert _rel_l2(res[True][1], res[False][1]) < 1e-4
+
+
+def test_guided_ddim_matches_oracle(cuda):
+    """val_guide (grad_through_unet=False) on a small UNet: render-loss guidance + langevin steps vs the oracle chain.
+    The UNet runs fp16 tensor-core GEMMs and guidance feeds its output back, so the comparison is relative-L2 on the code."""
+    params = rp.make_decoder_params('P', 11)
+    params['density_net.0.bias'] = params['density_net.0.bias'] + 1.5
+    spec = up.unet_spec(image_size=128, in_channels=18, base_channels=64, channels_cfg=(1, 2), resblocks_per_downsample=1,
+                        attention_res=(), num_heads=2)
+    sd = up.random_state_dict(spec, seed=4, std=0.03)
+    test_cfg = dict(num_timesteps=4, clip_range=[-2, 2], density_thresh=0.1, n_inverse_rays=2 ** 10, loss_coef=0.1 / (32 * 32),
+                    guidance_gain=0.4 * (2 ** 10), snr_weight_power=0.25, grad_through_unet=False, langevin_steps=1, langevin_delta=0.4,
+                    langevin_t_range=[0, 600], dt_gamma_scale=0.5)
+    model = _model(cuda, params, test_cfg, sd, spec)
+    B, res = 1, 32
+    g = torch.Generator().manual_seed(2)
+    noise = torch.randn(B, 3, 6, 128, 128, generator=g)
+    poses = torch.from_numpy(spiral_poses(1))[None]                          # [B,1,4,4]
+    f = 131.25 * res / 128
+    intr = torch.tensor([f, f, res / 2, res / 2]).expand(B, 1, 4).contiguous()
+    cond_imgs = torch.rand(B, 1, res, res, 3, generator=g)
+    with pytest.raises(NotImplementedError):                                  # the reference default needs the UNet backward (f1)
+        model.test_cfg['grad_through_unet'] = True
+        model.diffusion.test_cfg['grad_through_unet'] = True
+        model.val_guide(dict(cond_imgs=cond_imgs.to(cuda), cond_intrinsics=intr.to(cuda), cond_poses=poses.to(cuda), noise=noise.to(cuda)))
+    model.test_cfg['grad_through_unet'] = False
+    model.diffusion.test_cfg['grad_through_unet'] = False
+
+    # deterministic replicas of the random draws: langevin noise, perturb offsets and the occupancy jitter are injected
+    lang = [torch.randn(B, 18, 128, 128, generator=g) for _ in range(8)]
+    pert = [torch.rand(B, res * res, generator=g) for _ in range(16)]
+    jit = [torch.rand(64 ** 3, 3, generator=g) for _ in range(16)]
+    it = dict(l=iter(lang), p=iter(pert), j=iter(jit))
+    orig_loss, orig_ues, orig_lang = model.loss, model.update_extra_state, model.diffusion.p_sample_langevin
+    model.loss = lambda *a, **k: orig_loss(*a, **dict(k, perturb=next(it['p']).to(cuda)))
+    model.update_extra_state = lambda *a, **k: orig_ues(*a, **dict(k, jitter=next(it['j']).to(cuda)))
+    model.diffusion.p_sample_langevin = lambda x, t, **k: orig_lang(x, t, **dict(k, noise=next(it['l']).to(cuda)))
+    code_gpu, grid_gpu, bits_gpu = model.val_guide(dict(cond_imgs=cond_imgs.to(cuda), cond_intrinsics=intr.to(cuda), cond_poses=poses.to(cuda),
+                                                        noise=noise.to(cuda)))
+    # oracle chain
+    ro, rd = rp.get_cam_rays(poses, intr, res, res)
+    dtg = (0.5 / intr[..., :2].mean(dim=(-2, -1))).numpy()
+    grid = torch.zeros(B, 64 ** 3)
+    it2 = dict(p=iter(pert), j=iter(jit))
+
+    def grad_fn(x0):
+        code_pred = x0.reshape(B, 3, 6, 128, 128)
+        bits, _ = rp.update_extra_state(params, code_pred, grid, next(it2['j']), density_thresh=0.1, decay=0.9)
+        _, grad, _ = tp.render_loss_grad(params, code_pred, ro.reshape(B, -1, 3).numpy(), rd.reshape(B, -1, 3).numpy(),
+                                         cond_imgs.reshape(B, -1, 3).numpy(), bits, noises=next(it2['p']).numpy(), dt_gamma=dtg, bg_color=1.0,
+                                         pixel_weight=20.0, loss_coef=test_cfg['loss_coef'], scale_num_ray=res * res, reg_weight=3e-3)
+        return (grad * B).reshape(x0.shape).float()
+
+    dv = up.diffusion_vars(up.linear_betas())
+    ref = tp.guided_ddim_sample(lambda x, t: up.unet_forward(sd, spec, x, t), noise.reshape(B, 18, 128, 128), dv, grad_fn, num_timesteps=4,
+                                guidance_gain=test_cfg['guidance_gain'], snr_weight_power=0.25, langevin_steps=1, langevin_delta=0.4,
+                                langevin_t_range=(0, 600), langevin_noises=lang)
+    rel = _rel_l2(code_gpu.reshape(B, 18, 128, 128), ref)
+    assert rel < 2e-2, rel
+    # guidance actually moved the sample: the unguided run differs by much more than the tolerance
+    model.loss, model.update_extra_state, model.diffusion.p_sample_langevin = orig_loss, orig_ues, orig_lang
+    cfg0 = dict(test_cfg, langevin_steps=0)
+    model.diffusion.test_cfg = cfg0
+    plain = model.diffusion(noise.reshape(B, 18, 128, 128).to(cuda), return_loss=False)
+    assert _rel_l2(plain, ref) > 5 * rel
