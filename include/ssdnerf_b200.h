@@ -274,6 +274,9 @@ SSDNERF_API int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, ui
 SSDNERF_API int ssdnerf_im2col_s2(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream);
 /* nearest-neighbour x2 (DenoisingUpsample) */
 SSDNERF_API int ssdnerf_upsample2x(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream);
+/* fused attention: out[b][t][h*ch + d] = softmax_s(scale * q[b,t,h,:] . k[b,s,h,:]) v[b,s,h,d], scores kept on chip (flash-style);
+ * qkv fp16 [B][T][3*heads*ch] with the legacy head layout (modules.py:36-48), ch in {64, 128}, T % 64 == 0 */
+SSDNERF_API int ssdnerf_flash_attn(const void* qkv, uint32_t B, uint32_t T, uint32_t heads, uint32_t ch, float scale, void* out, void* stream);
 /* P = softmax(S) along the last axis; S fp32 [rows][T] -> P fp16 */
 SSDNERF_API int ssdnerf_softmax_rows(const float* S, uint32_t rows, uint32_t T, void* P, void* stream);
 /* Vt[b][h][c][t] = qkv[b][t][h*3ch + 2ch + c] (legacy head layout of modules.py:36-48) */

@@ -33,6 +33,25 @@ int set_error_msg(int code, const char* msg);
 
 __host__ __device__ inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): consecutive kernels of the DDIM step are launched with the programmatic-stream-serialization
+// attribute, so the next kernel's CTAs may start (barrier init, TMEM allocation, weight / bias staging) while the tail of the current
+// one drains.  pdl_wait() blocks until the preceding kernel has completed and its writes are visible: nothing produced by an earlier
+// kernel may be read, and nothing an earlier kernel reads may be written, before it.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();     // error.cu: SSDNERF_PDL=0 disables the attribute (A/B runs)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
 __device__ __forceinline__ float signf(float x) { return copysignf(1.0f, x); }
 

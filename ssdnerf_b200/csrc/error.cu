@@ -2,10 +2,16 @@
 #include "common.cuh"
 #include "../../include/ssdnerf_b200.h"
 #include <cstdio>
+#include <cstdlib>
 
 namespace ssdnerf {
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SSDNERF_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 void count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 
 int set_error(cudaError_t e, const char* what, const char* file, int line) {

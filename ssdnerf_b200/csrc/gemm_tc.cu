@@ -22,7 +22,9 @@
 namespace ssdnerf {
 using namespace tc;
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
+constexpr int kMaxBiasN = 2048;         // bias vector staged in shared memory once per CTA
 constexpr int kBM = 128, kBK = 64;
 constexpr int kABytes = kBM * kBK * 2;  // 16 KB
 
@@ -51,7 +53,8 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*quad-stat accumulators*/;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*quad-stat accumulators*/ +
+                                    kMaxBiasN * 4 /*bias*/;
 };
 
 // CL = cluster size along M: the CL CTAs of a cluster work on CL consecutive M tiles of the same N tile; each loads 1/CL of the
@@ -71,6 +74,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* qacc = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [2 images][BN/4][2]
+    float* sbias = qacc + 256;                                                               // [kMaxBiasN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
@@ -85,16 +89,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA1); prefetch_tmap(&mapA2); prefetch_tmap(&mapB);
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     for (int i = threadIdx.x; i < BN; i += kGemmThreads) qacc[i] = 0.0f;     // 2 * BN/4 * 2 floats
+    if (p.bias_n) for (uint32_t i = threadIdx.x; i < p.n_valid; i += kGemmThreads) sbias[i] = __ldg(p.bias_n + i);
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();       // peers' barriers are initialised before any multicast load / remote arrive targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched only shared memory, TMEM and constant weights (bias): it may overlap the tail of the preceding
+    // kernel; activations, residual, statistics and the output buffer are only touched after the dependency is resolved
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {   // ---------------- TMA producer
@@ -151,10 +160,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
             }
         }
         __syncwarp();
-    } else {   // ---------------- epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+    } else {   // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
         const uint32_t q = (uint32_t)warp & 3u;
+        const uint32_t hsel = (uint32_t)(warp - 2) >> 2;
+        constexpr int kChunks = BN / 64;                     // 32-column chunks per warp
         const uint32_t row = q * 32 + (uint32_t)lane;
         const uint32_t i1 = row % p.b1, i2 = (row / p.b1) % p.b2, i3 = row / (p.b1 * p.b2);
+        const bool has_bias = p.bias_n != nullptr;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
             const uint32_t m_tile = (tile % sup_m) * CL + crank, n_tile = tile / sup_m;
@@ -166,12 +178,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
             const uint32_t img = p.stats_hw ? g1 / p.stats_hw : g3;
             const uint32_t img0 = p.stats_hw ? (t1 * p.b1) / p.stats_hw : t3 * p.b3;
             const uint32_t slot = (img - img0) & 1u;
+            const uint32_t cbeg = hsel * (BN / 2);
+            // the residual does not depend on the accumulator: its loads are issued before the wait on the MMA (and one chunk ahead)
+            uint4 rcur[4], rnext[4];
+            auto fetch_res = [&](uint32_t c0, uint4* r) {
+                const bool ok = p.residual && row_ok && (n_tile * BN + c0 + 32 <= p.n_valid);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) r[g] = ok ? __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0) + g) : make_uint4(0, 0, 0, 0);
+            };
+            fetch_res(cbeg, rcur);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+#pragma unroll
+            for (int ci = 0; ci < kChunks; ++ci) {
+                const uint32_t c0 = cbeg + 32u * ci;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((q * 32u) << 16) + acc * BN + c0, v);
+                if (ci + 1 < kChunks) fetch_res(c0 + 32, rnext);
                 tmem_ld_wait();
                 const uint32_t ncol0 = n_tile * BN + c0;
                 float f[32];
@@ -179,24 +202,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                 for (int i = 0; i < 32; ++i) f[i] = 0.0f;
                 const bool live = row_ok && ncol0 < p.n_valid;
                 if (live) {
+                    const bool full32 = (ncol0 + 32 <= p.n_valid);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-                    if (p.bias_n) {
+                    if (has_bias) {
+                        if (full32) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) f[i] += __ldg(p.bias_n + ncol0 + i);
+                            for (int g = 0; g < 8; ++g) {
+                                const float4 b = *reinterpret_cast<const float4*>(sbias + ncol0 + 4 * g);
+                                f[4 * g] += b.x; f[4 * g + 1] += b.y; f[4 * g + 2] += b.z; f[4 * g + 3] += b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) f[i] += sbias[ncol0 + i];
+                        }
                     }
-                    const bool full32 = (ncol0 + 32 <= p.n_valid);
                     if (p.residual) {
-                        const __half* rp = p.residual + off + c0;
                         if (full32) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + g);
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[g]);
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h2[i]); f[8 * g + 2 * i] += t.x; f[8 * g + 2 * i + 1] += t.y; }
                             }
                         } else {
+                            const __half* rp = p.residual + off + c0;
                             for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) f[i] += __half2float(rp[i]);
                         }
                     }
@@ -224,7 +254,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                         }
                     }
                 }
-                if (p.qstats) {   // fused GroupNorm statistics of the (fp16-rounded) output: 8 quads x {sum, sumsq} per thread ...
+                if (p.qstats) {   // fused GroupNorm statistics of the fp32 output values: 8 quads x {sum, sumsq} per thread ...
                     float sv[16];
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
@@ -232,7 +262,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             float x = f[4 * q4 + e];
-                            if (!p.out_f32) x = __half2float(__float2half_rn(x));
                             if (!live || ncol0 + 4 * q4 + e >= p.n_valid) x = 0.0f;
                             su += x; sq = fmaf(x, x, sq);
                         }
@@ -255,21 +284,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                         atomicAdd(qacc + (slot * (BN / 4) + c0 / 4 + (idx & 7)) * 2 + (idx >> 3), sv[0]);
                     }
                 }
+                if (ci + 1 < kChunks) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
             if (p.qstats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const uint32_t et = threadIdx.x - 64;                 // 0..127 within the epilogue warps
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const uint32_t et = threadIdx.x - 64;                 // 0..255 within the epilogue warps
                 const uint32_t nq = p.n_valid / 4;
-                for (uint32_t i = et; i < (uint32_t)BN; i += 128) {      // i = (slot * BN/4 + quad) * 2 + stat
+                for (uint32_t i = et; i < (uint32_t)BN; i += kEpiThreads) {   // i = (slot * BN/4 + quad) * 2 + stat
                     const float val = qacc[i];
                     const uint32_t sl = i / (BN / 2), qd = (i % (BN / 2)) >> 1, st = i & 1u;
                     const uint32_t gq = n_tile * (BN / 4) + qd;
                     if (val != 0.0f && gq < nq) atomicAdd(p.qstats + ((size_t)(img0 + sl) * nq + gq) * 2 + st, val);
                     qacc[i] = 0.0f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -337,10 +370,12 @@ static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUt
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
     SSDNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL>, mA1, mA2, mB, p));
     SSDNERF_LAUNCH_OK();
     return 0;
@@ -387,6 +422,7 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     p.alpha = a->alpha; p.bias_n = a->bias_n; p.residual = (const __half*)a->residual; p.out = a->out; p.out_f32 = a->out_f32;
     p.so1 = a->so1; p.so2 = a->so2; p.so3 = a->so3;
     p.qstats = a->qstats; p.stats_hw = a->stats_hw;
+    if (a->bias_n && a->n > (uint32_t)kMaxBiasN) return set_error_msg(SSDNERF_ERR_ARG, "gemm: bias vectors longer than 2048 are not supported");
     if (a->qstats && (a->n % 4)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: quad statistics need n % 4 == 0");
     if (a->qstats && a->stats_hw && (a->stats_hw % 64)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: stats_hw must be a multiple of 64");
     const uint64_t ktot = (uint64_t)a->k1 + (a->a2 ? a->k2 : 0);

@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
 
 // ---------------------------------------------------------------- x fp32 [B,C,H,W] -> fp16 [B,H,W,Cpad]
 __global__ void k_nchw_to_nhwc(const float* __restrict__ x, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cpad, __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;   // over B*HW*(Cpad/8)
     const uint32_t cv = Cpad / 8;
     if (i >= (size_t)B * HW * cv) return;
@@ -47,6 +49,8 @@ __global__ void k_nchw_to_nhwc(const float* __restrict__ x, uint32_t B, uint32_t
 // grid (chunks, B); per-channel partial sums in registers -> shared -> one global atomic per (group, block)
 __global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x1, uint32_t C1, const __half* __restrict__ x2, uint32_t C2,
                                                   uint32_t HW, uint32_t groups, uint32_t pix_per_block, float* __restrict__ stats) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];   // [2][C]
     const uint32_t C = C1 + C2, cv = C / 8, cv1 = C1 / 8;
     const uint32_t b = blockIdx.y;
@@ -101,33 +105,49 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x1,
                                                   const float* __restrict__ stats2, int quad_stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   const float* __restrict__ scale_shift, long long ss_batch_stride, float eps, int do_silu,
                                                   __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t C = C1 + C2, cv = C / 8, cv1 = C1 / 8;
     const uint32_t b = blockIdx.y;
     const uint32_t v = threadIdx.x % cv, lane_p = threadIdx.x / cv, pstep = blockDim.x / cv;
     const uint32_t cpg = C / groups;
     const float inv_n = 1.0f / ((float)HW * (float)cpg);
     const float* ss = scale_shift ? scale_shift + (size_t)b * ss_batch_stride : nullptr;
-    float a[8], bb[8];
+    // per-channel affine parameters: independent loads, all in flight while the group statistics are reduced
+    float ga[8], be[8], sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const uint32_t c = v * 8 + k, g = c / cpg;
-        float sm, sq;
+        const uint32_t c = v * 8 + k;
+        ga[k] = __ldg(gamma + c); be[k] = __ldg(beta + c);
+        sc[k] = ss ? 1.0f + __ldg(ss + c) : 1.0f; sh[k] = ss ? __ldg(ss + C + c) : 0.0f;
+    }
+    // group mean / rstd of image b: one thread per group (groups <= 64 <= blockDim.x), shared through smem
+    __shared__ float2 s_mr[64];
+    if (threadIdx.x < groups) {
+        const uint32_t g = threadIdx.x;
+        float sm = 0.0f, sq = 0.0f;
         if (!quad_stats) {
             sm = __ldg(stats + ((size_t)b * groups + g) * 2); sq = __ldg(stats + ((size_t)b * groups + g) * 2 + 1);
         } else {   // sum the group's 4-channel quads; quads [0, C1/4) come from source 1, the rest from source 2
-            sm = 0.0f; sq = 0.0f;
-            const uint32_t q1n = C1 / 4, q2n = C2 / 4;
-            for (uint32_t qi = g * (cpg / 4); qi < (g + 1) * (cpg / 4); ++qi) {
-                const float* src_q = qi < q1n ? stats + ((size_t)b * q1n + qi) * 2 : stats2 + ((size_t)b * q2n + (qi - q1n)) * 2;
-                sm += __ldg(src_q); sq += __ldg(src_q + 1);
+            const uint32_t q1n = C1 / 4, q2n = C2 / 4, nq = cpg / 4;
+            for (uint32_t i = 0; i < nq; ++i) {
+                const uint32_t qi = g * nq + i;
+                const float2 t = __ldg(reinterpret_cast<const float2*>(qi < q1n ? stats + ((size_t)b * q1n + qi) * 2
+                                                                                  : stats2 + ((size_t)b * q2n + (qi - q1n)) * 2));
+                sm += t.x; sq += t.y;
             }
         }
         const float mean = sm * inv_n;
-        const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + eps);
-        float ak = rstd * __ldg(gamma + c);
-        float bk = __ldg(beta + c) - mean * ak;
-        if (ss) { const float sc = 1.0f + __ldg(ss + c); ak *= sc; bk = fmaf(bk, sc, __ldg(ss + C + c)); }
-        a[k] = ak; bb[k] = bk;
+        s_mr[g] = make_float2(mean, rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.0f) + eps));
+    }
+    __syncthreads();
+    float a[8], bb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float2 mr = s_mr[(v * 8 + k) / cpg];
+        const float ak = mr.y * ga[k];
+        const float bk = be[k] - mr.x * ak;
+        a[k] = ak * sc[k]; bb[k] = fmaf(bk, sc[k], sh[k]);
     }
     const __half* src = v < cv1 ? x1 + (size_t)b * HW * C1 + v * 8 : x2 + (size_t)b * HW * C2 + (v - cv1) * 8;
     const uint32_t cs = v < cv1 ? C1 : C2;
@@ -153,6 +173,8 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x1,
 
 // ---------------------------------------------------------------- stride-2 3x3 im2col: [B,H,W,C] -> [B,H/2,W/2,9C]
 __global__ void k_im2col_s2(const __half* __restrict__ x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t cv = C / 8, Ho = H / 2, Wo = W / 2;
     const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;   // over B*Ho*Wo*9*cv
     if (i >= (size_t)B * Ho * Wo * 9 * cv) return;
@@ -171,6 +193,8 @@ __global__ void k_im2col_s2(const __half* __restrict__ x, uint32_t B, uint32_t H
 
 // ---------------------------------------------------------------- nearest x2: [B,H,W,C] -> [B,2H,2W,C]
 __global__ void k_upsample2x(const __half* __restrict__ x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t cv = C / 8;
     const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;   // over B*2H*2W*cv
     if (i >= (size_t)B * 4 * H * W * cv) return;
@@ -184,6 +208,8 @@ __global__ void k_upsample2x(const __half* __restrict__ x, uint32_t B, uint32_t 
 
 // ---------------------------------------------------------------- softmax over rows of fp32 S [rows][T] -> fp16 P
 __global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ S, uint32_t rows, uint32_t T, __half* __restrict__ P) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row = blockIdx.x * 8 + warp;
     if (row >= rows) return;
@@ -208,6 +234,8 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ 
 
 // ---------------------------------------------------------------- Vt[b][h][c][t] = qkv[b][t][h*3ch + 2ch + c]
 __global__ void k_transpose_v(const __half* __restrict__ qkv, uint32_t B, uint32_t T, uint32_t heads, uint32_t ch, __half* __restrict__ vt) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __half tile[32][34];
     const uint32_t bh = blockIdx.z, b = bh / heads, h = bh % heads;
     const uint32_t t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -229,6 +257,8 @@ __global__ void k_transpose_v(const __half* __restrict__ qkv, uint32_t B, uint32
 __global__ void k_ddim_update(float* __restrict__ x_t, const float* __restrict__ v, uint32_t B, uint32_t C, uint32_t HW, uint32_t Cv,
                               const float* __restrict__ coef, const int* __restrict__ step_ptr, float clip_lo, float clip_hi, int clip,
                               float* __restrict__ x0_out, __half* __restrict__ next_in, uint32_t Cpad) {
+    pdl_trigger();
+    pdl_wait();
     const int step = step_ptr ? *step_ptr : 0;
     const float sa = coef[4 * step], s1 = coef[4 * step + 1], sp = coef[4 * step + 2], dc = coef[4 * step + 3];
     const size_t i = threadIdx.x + (size_t)blockIdx.x * blockDim.x;   // over B*HW
@@ -255,11 +285,16 @@ __global__ void k_ddim_update(float* __restrict__ x_t, const float* __restrict__
         if (next_in) reinterpret_cast<uint4*>(next_in + i * Cpad + c0)[0] = f_to_h8(o);
     }
 }
-__global__ void k_step_advance(int* step_ptr, int value, int set) { if (set) *step_ptr = value; else *step_ptr += value; }
+__global__ void k_step_advance(int* step_ptr, int value, int set) {
+    pdl_trigger();
+    pdl_wait();
+    if (set) *step_ptr = value; else *step_ptr += value; }
 
 // dst[c][:] = table[*step_ptr][:] for c < copies   (per-step time-embedding rows of the DDIM loop)
 __global__ void k_select_row(const float* __restrict__ table, uint32_t row_elems, const int* __restrict__ step_ptr,
                              float* __restrict__ dst, uint32_t copies) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
     if (i >= row_elems) return;
     const float v = table[(size_t)(*step_ptr) * row_elems + i];
@@ -279,7 +314,7 @@ int ssdnerf_nchw_to_nhwc_f16(const float* x, uint32_t B, uint32_t C, uint32_t H,
     CHK_ALIGN16(out, "nchw_to_nhwc");
     const size_t n = (size_t)B * H * W * (Cpad / 8);
     if (!n) return 0;
-    k_nchw_to_nhwc<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, B, C, H * W, Cpad, (__half*)out);
+    SSDNERF_CUDA_OK(launch_pdl(k_nchw_to_nhwc, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, B, C, H * W, Cpad, (__half*)out));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -299,8 +334,8 @@ int ssdnerf_gn_stats(const void* x1, uint32_t C1, const void* x2, uint32_t C2, u
     if (chunks > max_chunks) chunks = max_chunks;
     const uint32_t ppb = (HW + chunks - 1) / chunks;
     chunks = (HW + ppb - 1) / ppb;
-    k_gn_stats<<<dim3(chunks, B), threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0,
-                                                                                     HW, groups, ppb, stats);
+    SSDNERF_CUDA_OK(launch_pdl(k_gn_stats, dim3(dim3(chunks, B)), dim3(threads), 2 * C * sizeof(float), (cudaStream_t)stream, (const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0,
+                                                                                     HW, groups, ppb, stats));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -314,14 +349,15 @@ static int gn_apply_impl(const void* x1, uint32_t C1, const void* x2, uint32_t C
     if (!B || !HW) return 0;
     const uint32_t cv = C / 8;
     if (cv > 256) return set_error_msg(SSDNERF_ERR_ARG, "gn_apply: at most 2048 channels");
+    if (groups > 64) return set_error_msg(SSDNERF_ERR_ARG, "gn_apply: at most 64 groups");
     const uint32_t threads = cv * (256 / cv);
-    uint32_t chunks = (HW + 31) / 32;
+    uint32_t chunks = (HW + 7) / 8;
     const uint32_t max_chunks = (148 * 8 + B - 1) / B;
     if (chunks > max_chunks) chunks = max_chunks;
     const uint32_t ppb = (HW + chunks - 1) / chunks;
     chunks = (HW + ppb - 1) / ppb;
-    k_gn_apply<<<dim3(chunks, B), threads, 0, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0, HW, groups, ppb, stats,
-                                                                     stats2, quad, gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, (__half*)out);
+    SSDNERF_CUDA_OK(launch_pdl(k_gn_apply, dim3(dim3(chunks, B)), dim3(threads), 0, (cudaStream_t)stream, (const __half*)x1, C1, (const __half*)x2, x2 ? C2 : 0, HW, groups, ppb, stats,
+                                                                     stats2, quad, gamma, beta, scale_shift, ss_batch_stride, eps, do_silu, (__half*)out));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -347,7 +383,7 @@ int ssdnerf_im2col_s2(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_
     CHK_ALIGN16(x, "im2col_s2"); CHK_ALIGN16(out, "im2col_s2");
     const size_t n = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
     if (!n) return 0;
-    k_im2col_s2<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, B, H, W, C, (__half*)out);
+    SSDNERF_CUDA_OK(launch_pdl(k_im2col_s2, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, B, H, W, C, (__half*)out));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -357,7 +393,7 @@ int ssdnerf_upsample2x(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32
     CHK_ALIGN16(x, "upsample2x"); CHK_ALIGN16(out, "upsample2x");
     const size_t n = (size_t)B * 4 * H * W * (C / 8);
     if (!n) return 0;
-    k_upsample2x<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, B, H, W, C, (__half*)out);
+    SSDNERF_CUDA_OK(launch_pdl(k_upsample2x, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, B, H, W, C, (__half*)out));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -366,14 +402,14 @@ int ssdnerf_softmax_rows(const float* S, uint32_t rows, uint32_t T, void* P, voi
     if (T % 4) return set_error_msg(SSDNERF_ERR_ARG, "softmax_rows: T % 4 must be 0");
     CHK_ALIGN16(S, "softmax_rows");
     if (!rows) return 0;
-    k_softmax_rows<<<blocks_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(S, rows, T, (__half*)P);
+    SSDNERF_CUDA_OK(launch_pdl(k_softmax_rows, dim3(blocks_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, S, rows, T, (__half*)P));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
 
 int ssdnerf_transpose_v(const void* qkv, uint32_t B, uint32_t T, uint32_t heads, uint32_t ch, void* vt, void* stream) {
     if (!B || !T) return 0;
-    k_transpose_v<<<dim3((T + 31) / 32, (ch + 31) / 32, B * heads), dim3(32, 8), 0, (cudaStream_t)stream>>>((const __half*)qkv, B, T, heads, ch, (__half*)vt);
+    SSDNERF_CUDA_OK(launch_pdl(k_transpose_v, dim3(dim3((T + 31) / 32, (ch + 31) / 32, B * heads)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, (const __half*)qkv, B, T, heads, ch, (__half*)vt));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -384,8 +420,8 @@ int ssdnerf_ddim_update(float* x_t, const float* v, uint32_t B, uint32_t C, uint
     if (Cpad % 8 || Cpad < C) return set_error_msg(SSDNERF_ERR_ARG, "ddim_update: Cpad must be a multiple of 8 and >= C");
     const size_t n = (size_t)B * H * W;
     if (!n) return 0;
-    k_ddim_update<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x_t, v, B, C, H * W, Cv, coef, step_ptr, clip_lo, clip_hi, clip, x0_out,
-                                                                       (__half*)next_in, Cpad);
+    SSDNERF_CUDA_OK(launch_pdl(k_ddim_update, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, x_t, v, B, C, H * W, Cv, coef, step_ptr, clip_lo, clip_hi, clip, x0_out,
+                                                                       (__half*)next_in, Cpad));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
@@ -393,13 +429,13 @@ int ssdnerf_ddim_update(float* x_t, const float* v, uint32_t B, uint32_t C, uint
 int ssdnerf_select_row(const float* table, uint32_t row_elems, const int* step_ptr, float* dst, uint32_t copies, void* stream) {
     if (!table || !step_ptr || !dst) return set_error_msg(SSDNERF_ERR_ARG, "select_row: NULL argument");
     if (!row_elems || !copies) return 0;
-    k_select_row<<<blocks_for(row_elems, 256), 256, 0, (cudaStream_t)stream>>>(table, row_elems, step_ptr, dst, copies);
+    SSDNERF_CUDA_OK(launch_pdl(k_select_row, dim3(blocks_for(row_elems, 256)), dim3(256), 0, (cudaStream_t)stream, table, row_elems, step_ptr, dst, copies));
     SSDNERF_LAUNCH_OK();
     return 0;
 }
 
 int ssdnerf_step_counter(int* step_ptr, int value, int set, void* stream) {
-    k_step_advance<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr, value, set);
+    SSDNERF_CUDA_OK(launch_pdl(k_step_advance, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_ptr, value, set));
     SSDNERF_LAUNCH_OK();
     return 0;
 }

@@ -205,6 +205,7 @@ class UNetEngine:
 
     def __init__(self, m: DenoisingUnetMod, batch, device):
         self.m, self.B, self.dev = m, batch, torch.device(device)
+        self.flash_attention = True      # False: unfused scores -> softmax -> PV composition (A/B tests)
         self.H, self.W = m.image_size
         self.bufs = {}
         self.cin_total = m.in_channels + m.concat_cond_channels
@@ -345,12 +346,15 @@ class UNetEngine:
         L, s = N.lib(), N.stream_ptr()
         xn = self._gn(x, qx, None, None, d['g'], d['b'], self._buf(('xn', T, c), (B, H, W, c)), False)
         qkv = U.linear_f16(xn.view(B * T, c), d['wqkv'], bias=d['bqkv'], n=3 * c, out=self._buf(('qkv', T, c), (B * T, 3 * c)))
-        S = U.attn_scores(qkv.view(B, T, 3 * c), heads, scale=1.0 / math.sqrt(ch), out=self._buf(('S', T), (B, heads, T, T), torch.float32))
-        P = self._buf(('P', T), (B, heads, T, T))
-        N.check(L.ssdnerf_softmax_rows(N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(P), s))
-        vt = self._buf(('vt', T, c), (B, heads, ch, T))
-        N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
-        o = U.attn_pv(P, vt, out=self._buf(('o', T, c), (B, T, c)))
+        if self.flash_attention and ch in (64, 128) and T % 64 == 0:
+            o = U.flash_attn(qkv.view(B, T, 3 * c), heads, 1.0 / math.sqrt(ch), out=self._buf(('o', T, c), (B, T, c)))
+        else:   # unfused composition (scores -> softmax -> P V), kept for head widths / lengths the fused kernel does not cover
+            S = U.attn_scores(qkv.view(B, T, 3 * c), heads, scale=1.0 / math.sqrt(ch), out=self._buf(('S', T), (B, heads, T, T), torch.float32))
+            P = self._buf(('P', T), (B, heads, T, T))
+            N.check(L.ssdnerf_softmax_rows(N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(P), s))
+            vt = self._buf(('vt', T, c), (B, heads, ch, T))
+            N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
+            o = U.attn_pv(P, vt, out=self._buf(('o', T, c), (B, T, c)))
         qo = self._q(('attn_out', tag), c)
         return U.linear_f16(o.view(B * T, c), d['wproj'], bias=d['bproj'], residual=x.view(B * T, c), n=c,
                             out=self._buf(('attn_out', tag), (B * T, c)), qstats=qo, stats_hw=T).view(B, H, W, c), qo

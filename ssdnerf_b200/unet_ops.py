@@ -27,7 +27,13 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+GEMM_LOG = None     # set to a list to record (M, N, K, taps, bn, cluster, batched, fused_stats) of every launch (profiling scripts)
+
+
 def _launch(a):
+    if GEMM_LOG is not None:
+        GEMM_LOG.append(dict(M=int(a.d1) * int(a.d2) * int(a.d3), N=int(a.n), K=int(a.k1) + int(a.k2), taps=int(a.taps), bn=int(a.bn),
+                             cluster=int(a.cluster), batched=int(a.b_batched), qstats=bool(a.qstats), f32=int(a.out_f32)))
     N.check(N.lib().ssdnerf_gemm_f16(ctypes.byref(a), N.stream_ptr()))
 
 
@@ -168,4 +174,18 @@ def attn_pv(P, vt, out=None):
     g.out, g.out_f32 = out.data_ptr(), 0
     g.so1, g.so2, g.so3 = c, ch, T * c
     _launch(g)
+    return out
+
+
+def flash_attn(qkv, heads, scale, out=None):
+    """O[b,t,h*ch+d] = softmax_s(scale * q.k) v with the scores kept on chip (csrc/attention.cu). qkv fp16 [B,T,3c], legacy head layout."""
+    N.require_cuda(qkv)
+    B, T, c3 = qkv.shape
+    c = c3 // 3
+    ch = c // heads
+    assert qkv.is_contiguous() and qkv.dtype == torch.float16
+    if out is None:
+        out = torch.empty(B, T, c, dtype=torch.float16, device=qkv.device)
+    N.check(N.lib().ssdnerf_flash_attn(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.c_f32(scale), N.ptr(out),
+                                       N.stream_ptr()))
     return out
