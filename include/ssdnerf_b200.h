@@ -251,6 +251,7 @@ typedef struct ssdnerf_gemm_args {
     /* optional fused GroupNorm statistics of the output: qstats [images][n/4][2] += {sum, sum of squares} of every 4-channel quad
      * (caller zero-fills); image of a row = index along d3 (stats_hw == 0) or (index along d1) / stats_hw (flattened rows) */
     float* qstats; uint32_t stats_hw;
+    void* debug_cycles;      /* optional uint64[8] device counters (pipeline wait cycles per role, summed over CTAs); NULL in production */
 } ssdnerf_gemm_args;
 SSDNERF_API int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
 

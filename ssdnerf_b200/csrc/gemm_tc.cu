@@ -45,25 +45,40 @@ struct GemmParams {
     long long so1, so2, so3;    // output element strides of d1, d2, d3 (column stride 1)
     float* qstats;              // optional [images][n_valid/4][2]: per-image sum / sum-of-squares of every 4-channel quad of the output
     uint32_t stats_hw;          // > 0: image index of a row = (row index along d1) / stats_hw; 0: image index = index along d3
+    unsigned long long* prof;   // optional debug counters (clock cycles summed over CTAs): [0] producer wait-empty, [1] producer total,
+                                // [2] MMA wait-full, [3] MMA wait-tmem-empty, [4] MMA total, [5] epilogue wait-tmem-full, [6] epilogue total
 };
 
-template <int BN>
+// CL = cluster size and mode: 1 = single CTA; 2 = CTA pair (one M = 256 MMA over two SMs, each stages half of B);
+// 4 / 8 = multicast cluster (every CTA loads 1/CL of the B tile and multicasts it to all, own M = 128 MMAs)
+template <int BN, int CL>
 struct GemmCfg {
-    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr bool kPair = (CL == 2);
+    static constexpr int kMC = (CL >= 4) ? CL : 1;
+    static constexpr int kBRows = kPair ? BN / 2 : BN;     // B rows resident per CTA and stage
+    static constexpr int kBoxRowsB = kPair ? BN / 2 : BN / kMC;   // B rows fetched by ONE TMA instruction of this CTA
+    static constexpr int kBBytes = kBRows * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kStages = (192 * 1024 / kStageBytes) > 8 ? 8 : (192 * 1024 / kStageBytes);
+    static constexpr uint32_t kTxBytes = (kPair ? 2u : 1u) * kStageBytes;   // bytes credited to the (pair: leader's) full barrier per stage
     static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*quad-stat accumulators*/ +
                                     kMaxBiasN * 4 /*bias*/;
 };
 
-// CL = cluster size along M: the CL CTAs of a cluster work on CL consecutive M tiles of the same N tile; each loads 1/CL of the
-// B (weight) tile and TMA-multicasts it to all of them, so the L2 -> SM operand traffic per CTA drops from A + B to A + B/CL.
+// The large layers are bound by the chip-wide L2 -> SM operand bandwidth (~60 B/clk/SM when all SMs pull; profiles/r01_gemm_pipeline_*),
+// not by the tensor pipe: a 128 x BN tile re-fetches (128 + BN) x 128 B per 64-wide k-block.  Two ways to fetch less per flop:
+// CL = 4 / 8: the CL CTAs of a cluster work on CL consecutive M tiles of the same N tile; each fetches 1/CL of the B (weight) tile and
+//   TMA-multicasts it into every CTA's shared memory -> B traffic / CL (L2 de-duplicates by itself only up to ~4 concurrent readers).
+// CL = 2: CTA pair (two SMs of a TPC) on 2 consecutive M tiles of the same N tile with ONE tcgen05.mma.cta_group::2 of M = 256:
+// each CTA stages its own 128-row A tile and HALF of the B (weight) tile, the leader's MMA reads both halves, so the shared-memory
+// write + read traffic per SM and per MMA drops from A + B to A + B/2 -- the single-SM kernel is shared-memory-bandwidth bound
+// (an M = 128 MMA re-reads both operands every 64 (N = 128) / 128 (N = 256) cycles while TMA refills them).
 template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
           const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CL>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -81,6 +96,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     const uint32_t sup_m = (tiles_m + CL - 1) / CL;                 // super-tiles (CL M tiles) along M
     const uint32_t total_tiles = sup_m * p.tiles_n;                   // work items per cluster
     const uint32_t iters = p.taps * (p.kc1 + p.kc2);
+    constexpr bool kPair = Cfg::kPair;
+    constexpr int kMC = Cfg::kMC;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     const uint32_t tile0 = (CL > 1) ? cluster_id_x() : blockIdx.x;
     const uint32_t tile_step = (CL > 1) ? num_clusters_x() : gridDim.x;
@@ -88,11 +105,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA1); prefetch_tmap(&mapA2); prefetch_tmap(&mapB);
-        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kMC); }   // multicast: every CTA's MMA releases the stage
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads * (kPair ? 2 : 1)); }   // pair: both epilogues free the leader's
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if (warp == 1) { if (kPair) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
     for (int i = threadIdx.x; i < BN; i += kGemmThreads) qacc[i] = 0.0f;     // 2 * BN/4 * 2 floats
     if (p.bias_n) for (uint32_t i = threadIdx.x; i < p.n_valid; i += kGemmThreads) sbias[i] = __ldg(p.bias_n + i);
     tc_fence_before();
@@ -106,8 +123,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {   // ---------------- TMA producer
+        {   // ---------------- TMA producer: the whole warp runs the loop converged, one elected lane issues (see tc_common.cuh)
             uint32_t stage = 0, phase = 0;
+            long long pw = 0; const long long pt0 = clock64();
             for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
                 const uint32_t m_tile = (tile % sup_m) * CL + crank, n_tile = tile / sup_m;     // m_tile may be >= tiles_m in the last
                 const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);   // super-tile: loads zero-fill
@@ -115,48 +133,67 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                     const int ox = (p.taps == 9) ? (int)(tap % 3) - 1 : 0;
                     const int oy = (p.taps == 9) ? (int)(tap / 3) - 1 : 0;
                     for (uint32_t j = 0; j < p.kc1 + p.kc2; ++j) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                        if (p.prof) { const long long c = clock64(); mbar_wait(&empty[stage], phase ^ 1); pw += clock64() - c; }
+                        else mbar_wait(&empty[stage], phase ^ 1);
                         const bool first = j < p.kc1;
-                        tma_load_4d(sA + stage * kABytes, first ? &mapA1 : &mapA2, &full[stage],
-                                    (int)((first ? j : j - p.kc1) * kBK), (int)(t1 * p.b1) + ox, (int)(t2 * p.b2) + oy,
-                                    (int)(t3 * p.b3));
+                        const int ak = (int)((first ? j : j - p.kc1) * kBK), a1 = (int)(t1 * p.b1) + ox, a2 = (int)(t2 * p.b2) + oy, a3 = (int)(t3 * p.b3);
                         if (CL == 1) {
-                            tma_load_4d(sB + stage * Cfg::kBBytes, &mapB, &full[stage], (int)(j * kBK), (int)(n_tile * BN),
-                                        p.b_batched ? (int)t2 : (int)tap, p.b_batched ? (int)t3 : 0);
-                        } else {   // this CTA's 1/CL slice of the B tile, broadcast to the whole cluster
-                            constexpr int kSlice = BN / CL;
-                            tma_load_4d_mc(sB + stage * Cfg::kBBytes + crank * kSlice * 128, &mapB, &full[stage], (int)(j * kBK),
-                                           (int)(n_tile * BN + crank * kSlice), (int)tap, 0, kMask);
+                            mbar_expect_tx_w(&full[stage], Cfg::kTxBytes);
+                            tma_load_4d_w(sA + stage * kABytes, first ? &mapA1 : &mapA2, &full[stage], ak, a1, a2, a3);
+                            tma_load_4d_w(sB + stage * Cfg::kBBytes, &mapB, &full[stage], (int)(j * kBK), (int)(n_tile * BN),
+                                          p.b_batched ? (int)t2 : (int)tap, p.b_batched ? (int)t3 : 0);
+                        } else if (kMC > 1) {   // own A tile + this CTA's 1/CL slice of the B tile broadcast to the whole cluster
+                            mbar_expect_tx_w(&full[stage], Cfg::kTxBytes);
+                            tma_load_4d_w(sA + stage * kABytes, first ? &mapA1 : &mapA2, &full[stage], ak, a1, a2, a3);
+                            tma_load_4d_mc_w(sB + stage * Cfg::kBBytes + crank * Cfg::kBoxRowsB * 128, &mapB, &full[stage], (int)(j * kBK),
+                                             (int)(n_tile * BN + crank * Cfg::kBoxRowsB), (int)tap, 0, kMask);
+                        } else {   // pair: own A tile + own half of the B tile, all bytes credited to the leader's barrier
+                            if (crank == 0) mbar_expect_tx_w(&full[stage], Cfg::kTxBytes);
+                            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+                            tma_load_4d_2cta_w(sA + stage * kABytes, first ? &mapA1 : &mapA2, lbar, ak, a1, a2, a3);
+                            tma_load_4d_2cta_w(sB + stage * Cfg::kBBytes, &mapB, lbar, (int)(j * kBK), (int)(n_tile * BN + crank * Cfg::kBRows),
+                                               (int)tap, 0);
                         }
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
+            if (p.prof && lane == 0) { atomicAdd(p.prof + 0, (unsigned long long)pw); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0)); }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {   // ---------------- MMA issuer
-            constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+        if (!kPair || crank == 0) {   // ---------------- MMA issuer: converged warp, elected lane issues (pair: the leader CTA issues for both SMs)
+            constexpr uint32_t idesc = make_idesc_f16(kBM * (kPair ? 2 : 1), BN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            long long wf = 0, we = 0; const long long mt0 = clock64();
             for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                const long long c0 = p.prof ? clock64() : 0;
+                if (kPair) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1); else mbar_wait(&tempty[acc], acc_phase ^ 1);
+                if (p.prof) we += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (uint32_t it = 0; it < iters; ++it) {
-                    mbar_wait(&full[stage], phase);
+                    if (p.prof) { const long long c = clock64(); mbar_wait(&full[stage], phase); wf += clock64() - c; }
+                    else mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = make_desc_sw128(smem_u32(sA + stage * kABytes));
                     const uint64_t b_desc = make_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
-                    for (uint32_t k = 0; k < kBK / 16; ++k)   // advance 16 halves = 32 B = 2 descriptor units along K
-                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
-                    if (CL == 1) umma_commit(&empty[stage]);
-                    else umma_commit_mc(&empty[stage], kMask);     // frees this stage in every CTA that multicasts into it
+                    for (uint32_t k = 0; k < kBK / 16; ++k) {   // advance 16 halves = 32 B = 2 descriptor units along K
+                        if (kPair) umma_f16_2cta_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+                        else umma_f16_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+                    }
+                    if (kPair) umma_commit_2cta_w(&empty[stage], kMask);        // frees this stage in both CTAs
+                    else if (kMC > 1) umma_commit_mc_w(&empty[stage], kMask);   // one of the CL releases every CTA's producer waits for
+                    else umma_commit_w(&empty[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (kPair) umma_commit_2cta_w(&tfull[acc], kMask); else umma_commit_w(&tfull[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (p.prof && lane == 0) {
+                atomicAdd(p.prof + 2, (unsigned long long)wf); atomicAdd(p.prof + 3, (unsigned long long)we);
+                atomicAdd(p.prof + 4, (unsigned long long)(clock64() - mt0));
             }
         }
         __syncwarp();
@@ -168,6 +205,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
         const uint32_t i1 = row % p.b1, i2 = (row / p.b1) % p.b2, i3 = row / (p.b1 * p.b2);
         const bool has_bias = p.bias_n != nullptr;
         uint32_t acc = 0, acc_phase = 0;
+        long long ew = 0; const long long et0 = clock64();
         for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
             const uint32_t m_tile = (tile % sup_m) * CL + crank, n_tile = tile / sup_m;
             const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);
@@ -187,7 +225,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                 for (int g = 0; g < 4; ++g) r[g] = ok ? __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0) + g) : make_uint4(0, 0, 0, 0);
             };
             fetch_res(cbeg, rcur);
-            mbar_wait(&tfull[acc], acc_phase);
+            if (p.prof) { const long long c = clock64(); mbar_wait(&tfull[acc], acc_phase); ew += clock64() - c; }
+            else mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll
             for (int ci = 0; ci < kChunks; ++ci) {
@@ -290,7 +329,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]);
             if (p.qstats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const uint32_t et = threadIdx.x - 64;                 // 0..255 within the epilogue warps
@@ -306,11 +345,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.prof && threadIdx.x == 64) { atomicAdd(p.prof + 5, (unsigned long long)ew); atomicAdd(p.prof + 6, (unsigned long long)(clock64() - et0)); }
     }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();       // nobody exits while a peer may still multicast into its shared memory
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+    if (warp == 1) { tc_fence_after(); if (kPair) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
 // ---------------------------------------------------------------- host side: tensor maps
@@ -355,7 +395,7 @@ static int make_map_4d(CUtensorMap* m, const void* base, uint64_t K, uint64_t e1
 template <int BN, int CL>
 static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const GemmParams& p, int sms,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CL>;
     static bool attr = false;
     if (!attr) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
@@ -363,10 +403,7 @@ static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUt
     }
     const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
     const uint32_t total = ((tiles_m + CL - 1) / CL) * p.tiles_n;          // work items per cluster (CL = 1: per CTA)
-    const uint32_t max_clusters = (uint32_t)sms / CL;
-    const uint32_t clusters = total < max_clusters ? total : max_clusters;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(clusters * CL);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmem;
     cfg.stream = stream;
@@ -376,6 +413,21 @@ static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUt
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 2;
+    static int max_clusters_cached = 0;      // co-resident clusters of this instantiation (1 CTA / SM; GPC sizes limit clusters of 4 / 8)
+    if (!max_clusters_cached) {
+        max_clusters_cached = sms / CL;
+        if (CL > 2) {
+            cfg.gridDim = dim3((uint32_t)(sms / CL) * CL);
+            int n = 0;
+            cfg.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<BN, CL>, &cfg) == cudaSuccess && n > 0 && n < max_clusters_cached) max_clusters_cached = n;
+            cfg.numAttrs = 2;
+            (void)cudaGetLastError();
+        }
+    }
+    const uint32_t max_clusters = (uint32_t)max_clusters_cached;
+    const uint32_t clusters = total < max_clusters ? total : max_clusters;
+    cfg.gridDim = dim3(clusters * CL);
     SSDNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, CL>, mA1, mA2, mB, p));
     SSDNERF_LAUNCH_OK();
     return 0;
@@ -421,7 +473,7 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     p.taps = a->taps; p.kc1 = a->k1 / 64; p.kc2 = a->a2 ? a->k2 / 64 : 0; p.n_valid = a->n; p.b_batched = a->b_batched;
     p.alpha = a->alpha; p.bias_n = a->bias_n; p.residual = (const __half*)a->residual; p.out = a->out; p.out_f32 = a->out_f32;
     p.so1 = a->so1; p.so2 = a->so2; p.so3 = a->so3;
-    p.qstats = a->qstats; p.stats_hw = a->stats_hw;
+    p.qstats = a->qstats; p.stats_hw = a->stats_hw; p.prof = (unsigned long long*)a->debug_cycles;
     if (a->bias_n && a->n > (uint32_t)kMaxBiasN) return set_error_msg(SSDNERF_ERR_ARG, "gemm: bias vectors longer than 2048 are not supported");
     if (a->qstats && (a->n % 4)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: quad statistics need n % 4 == 0");
     if (a->qstats && a->stats_hw && (a->stats_hw % 64)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: stats_hw must be a multiple of 64");
@@ -434,15 +486,26 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     } else {
         mA2 = mA1;
     }
-    // cluster of 2 along M with multicast of the weight tile: only for non-batched B and problems with >= 2 waves of M tiles
+    // clusters along M (weights shared): only for non-batched B.  The operand pipeline is latency-bound (shared-memory stages x bytes per
+    // stage / ~3300-cycle load round trip, profiles/r01_gemm_pipeline_*): what helps is more flops per staged byte, i.e. the CTA pair with
+    // N = 256 (each SM stages 128 + 128 rows for a 256 x 256 x 64 product); multicast clusters cut L2 traffic but not staged bytes and
+    // measured slower.  auto = pair for N = 256 tiles with >= 2 waves of M tiles.
     const uint32_t tiles_m_all = p.T1 * p.T2 * p.T3;
-    int cl = (!a->b_batched && a->cluster != 1 && bn >= 128 && tiles_m_all * p.tiles_n >= 2u * (uint32_t)sms) ? 2 : 1;
-    if (a->cluster == 2 && !a->b_batched && bn >= 128) cl = 2;
-    // B: {K, N, x2, x3}; box {64, bn / cl, 1, 1}
+    int cl = (!a->b_batched && a->cluster == 0 && bn == 256 && tiles_m_all * p.tiles_n >= 2u * (uint32_t)sms) ? 2 : 1;
+    if ((a->cluster == 2 || a->cluster == 4 || a->cluster == 8) && !a->b_batched && bn >= 128) cl = (int)a->cluster;
+    // B: {K, N, x2, x3}; box {64, rows fetched per TMA instruction (bn: single CTA, bn / 2: pair, bn / cl: multicast slice), 1, 1}
     if (int e = make_map_4d(&mB, a->b, ktot, a->n_rows_b ? a->n_rows_b : a->n, a->bx2 ? a->bx2 : 1, a->bx3 ? a->bx3 : 1, a->b_strides[0],
                             a->b_strides[1], a->b_strides[2], (uint32_t)(bn / cl), 1, 1)) return e;
 
-    if (bn == 256) return cl == 2 ? launch_gemm<256, 2>(mA1, mA2, mB, p, sms, stream) : launch_gemm<256, 1>(mA1, mA2, mB, p, sms, stream);
-    if (bn == 128) return cl == 2 ? launch_gemm<128, 2>(mA1, mA2, mB, p, sms, stream) : launch_gemm<128, 1>(mA1, mA2, mB, p, sms, stream);
+    if (bn == 256) {
+        if (cl == 8) return launch_gemm<256, 8>(mA1, mA2, mB, p, sms, stream);
+        if (cl == 4) return launch_gemm<256, 4>(mA1, mA2, mB, p, sms, stream);
+        return cl == 2 ? launch_gemm<256, 2>(mA1, mA2, mB, p, sms, stream) : launch_gemm<256, 1>(mA1, mA2, mB, p, sms, stream);
+    }
+    if (bn == 128) {
+        if (cl == 8) return launch_gemm<128, 8>(mA1, mA2, mB, p, sms, stream);
+        if (cl == 4) return launch_gemm<128, 4>(mA1, mA2, mB, p, sms, stream);
+        return cl == 2 ? launch_gemm<128, 2>(mA1, mA2, mB, p, sms, stream) : launch_gemm<128, 1>(mA1, mA2, mB, p, sms, stream);
+    }
     return launch_gemm<64, 1>(mA1, mA2, mB, p, sms, stream);
 }

@@ -23,14 +23,17 @@ class GemmArgs(ctypes.Structure):
         ('b_batched', N.c_u32),
         ('bn', N.c_u32), ('cluster', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
         ('out', N.c_void_p), ('out_f32', N.c_u32), ('so1', c_ll), ('so2', c_ll), ('so3', c_ll),
-        ('qstats', N.c_void_p), ('stats_hw', N.c_u32),
+        ('qstats', N.c_void_p), ('stats_hw', N.c_u32), ('debug_cycles', N.c_void_p),
     ]
 
 
+GEMM_PROF = None    # set to a uint64[8] CUDA tensor to collect per-role pipeline wait cycles (debug)
 GEMM_LOG = None     # set to a list to record (M, N, K, taps, bn, cluster, batched, fused_stats) of every launch (profiling scripts)
 
 
 def _launch(a):
+    if GEMM_PROF is not None:
+        a.debug_cycles = GEMM_PROF.data_ptr()
     if GEMM_LOG is not None:
         GEMM_LOG.append(dict(M=int(a.d1) * int(a.d2) * int(a.d3), N=int(a.n), K=int(a.k1) + int(a.k2), taps=int(a.taps), bn=int(a.bn),
                              cluster=int(a.cluster), batched=int(a.b_batched), qstats=bool(a.qstats), f32=int(a.out_f32)))

@@ -68,7 +68,7 @@ def test_batched_attention_gemms(cuda):
     _check(S, ref, 1e-3)
 
 
-@pytest.mark.parametrize('cluster', [1, 2])
+@pytest.mark.parametrize('cluster', [1, 2, 4, 8])
 @pytest.mark.parametrize('B,H,W,Cin,Cout,bn', [(3, 64, 64, 128, 256, 256), (2, 128, 128, 64, 128, 128), (5, 8, 8, 512, 512, 256), (1, 32, 32, 256, 256, 128)])
 def test_conv3x3_cluster_multicast(cuda, cluster, B, H, W, Cin, Cout, bn):
     """CTA pairs along M with TMA multicast of the weight tile (odd tile counts exercise the zero-filled tail CTA)"""
