@@ -252,6 +252,7 @@ typedef struct ssdnerf_gemm_args {
      * (caller zero-fills); image of a row = index along d3 (stats_hw == 0) or (index along d1) / stats_hw (flattened rows) */
     float* qstats; uint32_t stats_hw;
     void* debug_cycles;      /* optional uint64[8] device counters (pipeline wait cycles per role, summed over CTAs); NULL in production */
+    uint32_t algo;           /* 0 = auto, 1 = generic tile kernel, 2 = row-pair 3x3 convolution (128-pixel rows, 128 output channels) */
 } ssdnerf_gemm_args;
 SSDNERF_API int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
 

@@ -392,6 +392,12 @@ static int make_map_4d(CUtensorMap* m, const void* base, uint64_t K, uint64_t e1
     return 0;
 }
 
+int make_map_4d_box(CUtensorMap* m, const void* base, uint64_t K, uint64_t e1, uint64_t e2, uint64_t e3, uint64_t s1, uint64_t s2, uint64_t s3,
+                    uint32_t x1, uint32_t x2, uint32_t x3) {
+    return make_map_4d(m, base, K, e1, e2, e3, s1, s2, s3, x1, x2, x3);
+}
+int conv_row2_launch(const ssdnerf_gemm_args* a, int sms, cudaStream_t stream);   // conv_row2.cu
+
 template <int BN, int CL>
 static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const GemmParams& p, int sms,
                        cudaStream_t stream) {
@@ -448,6 +454,12 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     int dev = 0, sms = 0;
     SSDNERF_CUDA_OK(cudaGetDevice(&dev));
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // 3x3 convolution over 128-pixel rows with 128 output channels (the UNet's 128 x 128 level): row-pair kernel with halo reuse
+    if (a->algo != 1 && a->taps == 9 && a->d1 == 128 && a->b1 == 128 && a->b2 == 1 && a->b3 == 1 && a->n == 128 && !a->out_f32 && !a->b_batched &&
+        (a->d2 % 2) == 0 && a->alpha == 1.0f && (a->bn == 0 || a->bn == 128) && a->cluster <= 1 && a->so1 == 128 && a->so2 == 128 * 128 &&
+        a->so3 == (long long)a->d2 * 128 * 128 && (!a->qstats || a->stats_hw == 0) && (a->n_rows_b == 0 || a->n_rows_b >= 128))
+        return ssdnerf::conv_row2_launch(a, sms, stream);
+    if (a->algo == 2) return set_error_msg(SSDNERF_ERR_ARG, "gemm: algo 2 (row-pair convolution) needs taps 9, 128-pixel rows, 128 output channels, fp16 output");
     int bn = (int)a->bn;
     if (!bn) {
         // pick the N tile that minimises (waves x tile cost): wide tiles amortise A loads (N=256 runs the MMA pipe at full rate,

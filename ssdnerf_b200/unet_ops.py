@@ -23,7 +23,7 @@ class GemmArgs(ctypes.Structure):
         ('b_batched', N.c_u32),
         ('bn', N.c_u32), ('cluster', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
         ('out', N.c_void_p), ('out_f32', N.c_u32), ('so1', c_ll), ('so2', c_ll), ('so3', c_ll),
-        ('qstats', N.c_void_p), ('stats_hw', N.c_u32), ('debug_cycles', N.c_void_p),
+        ('qstats', N.c_void_p), ('stats_hw', N.c_u32), ('debug_cycles', N.c_void_p), ('algo', N.c_u32),
     ]
 
 
@@ -99,7 +99,7 @@ def _conv_boxes(H, W):
     return bw, bh, nb
 
 
-def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0, cluster=0, qstats=None):
+def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f32=False, taps=9, bn=0, cluster=0, qstats=None, algo=0):
     """3x3 (taps=9, pad 1, stride 1) or 1x1 (taps=1) convolution over NHWC fp16 x [B,H,W,C1] (+ x2 [B,H,W,C2] concatenated
     along channels).  wp: packed weight [taps][Cout_pad][C1+C2]."""
     N.require_cuda(x, wp)
@@ -122,7 +122,7 @@ def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f3
     rows = wp.shape[-2]
     g.b, g.n, g.n_rows_b, g.bx2, g.bx3 = wp.data_ptr(), cout, rows, taps, 1
     g.b_strides = (c_u64 * 3)(ktot * 2, rows * ktot * 2, taps * rows * ktot * 2)
-    g.bn, g.alpha, g.cluster = bn, 1.0, cluster
+    g.bn, g.alpha, g.cluster, g.algo = bn, 1.0, cluster, algo
     g.bias_n = bias.data_ptr() if bias is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)

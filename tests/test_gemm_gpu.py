@@ -91,3 +91,29 @@ def test_plain_gemm_cluster(cuda):
     w = (torch.randn(N, K, generator=g) * 0.1).half().to(cuda)
     out = U.linear_f16(a, w, bn=256, cluster=2)
     _check(out, a.float() @ w.float().t())
+
+
+@pytest.mark.parametrize('B,H,C1,C2', [(2, 8, 128, 0), (1, 128, 64, 0), (3, 6, 128, 128), (2, 4, 256, 128)])
+def test_conv3x3_row_pair_kernel(cuda, B, H, C1, C2):
+    """128-pixel-wide rows, 128 output channels: row-pair kernel with halo reuse (algo 2) == generic tile kernel (algo 1) == fp32 conv,
+    including image borders, the skip-concat second input, bias, residual and the fused quad statistics"""
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(B * 100 + H + C1 + C2)
+    W, Cout = 128, 128
+    x = torch.randn(B, H, W, C1, generator=g).half().to(cuda)
+    x2 = torch.randn(B, H, W, C2, generator=g).half().to(cuda) if C2 else None
+    w = torch.randn(Cout, C1 + C2, 3, 3, generator=g) * 0.05
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    res = torch.randn(B, H, W, Cout, generator=g).half().to(cuda)
+    wp = U.pack_conv_weight(w).to(cuda)
+    outs, stats = {}, {}
+    for algo in (1, 2):
+        q = torch.zeros(B, Cout // 4, 2, device=cuda)
+        outs[algo] = U.conv3x3_f16(x, wp, Cout, bias=bias, x2=x2, residual=res, qstats=q, algo=algo)
+        stats[algo] = q
+    xin = torch.cat([x, x2], dim=-1) if C2 else x
+    ref = torch.nn.functional.conv2d(xin.float().permute(0, 3, 1, 2), w.half().float().to(cuda), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(outs[2], ref)
+    _check(outs[1], ref)
+    torch.testing.assert_close(outs[2].float(), outs[1].float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(stats[2], stats[1], rtol=1e-3, atol=5e-2)
