@@ -223,6 +223,41 @@ def run_ours(args):
                        img_hw=(IMG, IMG), want_blend=False)['num_samples']
     samples = int(cnt.sum().item())
 
+    # ---- side measurement (not part of the timed step): north_star's synthetic "random-init 3x32x128x128 triplane" workload through the
+    # class-default decoder (variant S: hidden 128, colour net 144 -> 128 -> 3), 32 views x 128^2 per scene, this rank's GPU only
+    side_S = None
+    if args.side_s and rank == 0:
+        dec_s = S.build_module(dict(type='TriPlaneDecoder', max_steps=256)).to(dev).eval()
+        with torch.no_grad():
+            dec_s.density_net[0].bias += 1.0
+        gs = torch.Generator().manual_seed(77)
+        code_s = (torch.randn(B, 3, 32, 128, 128, generator=gs) * 0.5).to(dev)
+        vs = R.DEC_S
+        planes_s = R.pack_planes(code_s, vs)
+        from ssdnerf_b200 import density as Dm
+        _, bits_s = Dm.get_density(vs, planes_s, (128, 128), dec_s.packed_blob(), B, density_thresh=0.1, grid_size=64, bound=1.0)
+        Vs = min(32, V)
+
+        def render_s(counts=False):
+            return R.render_fwd(vs, planes_s, (128, 128), bits_s, dec_s.packed_blob(), poses=poses[:, :Vs].contiguous(),
+                                intrinsics=intr[:, :Vs].contiguous(), img_hw=(IMG, IMG), want_blend=True, want_counts=counts)
+        for _ in range(2):
+            render_s()
+        torch.cuda.synchronize(dev)
+        a0, a1 = ev(), ev()
+        a0.record(stream)
+        for _ in range(3):
+            render_s()
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms_s = a0.elapsed_time(a1) / 3
+        n_s = int(render_s(True)['num_samples'].sum().item())
+        rays_s = B * Vs * IMG * IMG
+        side_S = {'workload': f'random-init 3x32x128x128 triplanes, class-default decoder (variant S), {B} scenes x {Vs} views x {IMG}x{IMG}, 1 GPU',
+                  'rays_per_sec': rays_s / (ms_s * 1e-3), 'samples_per_sec': n_s / (ms_s * 1e-3), 'ms': ms_s, 'samples_per_ray': n_s / rays_s,
+                  'kernel': 'k_render_s2 (fp16 planes, warp-level mma.sync MLP)', 'flops_per_sample': 62464,
+                  'tflops': n_s * 62464 / (ms_s * 1e-3) / 1e12}
+
     # ---- reduce over ranks (max time)
     times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms], device=dev, dtype=torch.float64)
     samples_t = torch.tensor([samples], device=dev, dtype=torch.float64)
@@ -272,9 +307,12 @@ def run_ours(args):
         'roofline_unet': {'kernel': 'k_gemm_tc (tcgen05 implicit-GEMM conv / GEMM) + glue, timed as the whole DDIM stage', 'bound': 'tensor',
                           'achieved': tf_achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': tf_achieved / pk['tf_sustained'],
                           'peak_source': f"{pk['src']} (sustained cuBLAS bf16)",
-                          'note': 'large convs alone run at 1.2-1.3 PFLOP/s (profiles/r01_gemm_conv_microbench.txt); GroupNorm/attention glue and '
-                                  'the 8x8/16x16 levels pull the stage average down'},
+                          'note': 'per-layer table: profiles/r01_unet_layer_table.txt (128x128- and 64x64-level convs 1.0-1.5 PFLOP/s; the operand '
+                                  'pipeline of one SM saturates at ~58 B/clk, profiles/r01_gemm_pipeline_prof.txt); GroupNorm-apply passes, '
+                                  'attention and the latency-bound 8x8/16x16 levels pull the stage average down'},
     }
+    if side_S is not None:
+        line['render_variant_S'] = side_S
     if args.cpu_baseline:
         line['cpu_baseline'] = cpu_reference_sample(quick=True)
     print(json.dumps(line))
@@ -365,6 +403,7 @@ def main():
     ap.add_argument('--batch', type=int, default=B_PER_GPU)
     ap.add_argument('--views', type=int, default=NUM_VIEWS)
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    ap.add_argument('--no-side-s', dest='side_s', action='store_false', help='skip the variant-S renderer side measurement')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3      # timing rule: at least 3 warm-up steps
