@@ -11,10 +11,11 @@
 #include "common.cuh"
 #include "../../include/ssdnerf_b200.h"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace ssdnerf {
 
-constexpr int kFaWarps = 4, kFaThreads = kFaWarps * 32, kFaBM = 64, kFaBN = 64;
+constexpr int kFaBN = 64;      // keys per shared-memory tile; queries per CTA = 16 per warp, WARPS in {4, 8}
 
 __device__ __forceinline__ void fa_cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
@@ -34,18 +35,20 @@ __device__ __forceinline__ void fa_mma(float* d, const uint32_t* a, uint32_t b0,
 __device__ __forceinline__ uint32_t fa_pack(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
 __device__ __forceinline__ float fa_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// grid (T / 64, B * heads); qkv fp16 [B][T][3 * heads * CH]; out fp16 [B][T][heads * CH]
-template <int CH>
-__global__ void __launch_bounds__(kFaThreads) k_flash_attn(const __half* __restrict__ qkv, uint32_t T, uint32_t heads, float scale_log2,
+// grid (T / (16 WARPS), B * heads); qkv fp16 [B][T][3 * heads * CH]; out fp16 [B][T][heads * CH]
+template <int CH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_flash_attn(const __half* __restrict__ qkv, uint32_t T, uint32_t heads, float scale_log2,
                                                            __half* __restrict__ out) {
+    constexpr int kFaThreads = WARPS * 32, kFaBM = WARPS * 16;
     constexpr int kRow = CH * 2 + 16;                 // bytes per smem row (16 B pad: conflict-free ldmatrix)
-    constexpr int kTile = kFaBN * kRow;               // one 64-row tile
+    constexpr int kTile = kFaBN * kRow;               // one 64-row K / V tile
+    constexpr int kQBytes = kFaBM * kRow;
     constexpr int kKC = CH / 16;                      // k-chunks of the QK^T product
     constexpr int kVec = CH / 8;                      // 16-byte vectors per row
     extern __shared__ __align__(16) unsigned char fa_smem[];
-    unsigned char* sQ = fa_smem;                      // [64][kRow]
-    unsigned char* sK = fa_smem + kTile;              // [2][64][kRow]
-    unsigned char* sV = fa_smem + 3 * kTile;          // [2][64][kRow]
+    unsigned char* sQ = fa_smem;                      // [16 WARPS][kRow]
+    unsigned char* sK = fa_smem + kQBytes;            // [2][64][kRow]
+    unsigned char* sV = sK + 2 * kTile;               // [2][64][kRow]
 
     pdl_trigger();
     pdl_wait();
@@ -55,15 +58,15 @@ __global__ void __launch_bounds__(kFaThreads) k_flash_attn(const __half* __restr
     const size_t c3 = (size_t)3 * heads * CH;
     const __half* base = qkv + (size_t)b * T * c3 + (size_t)h * 3 * CH;       // q of this head; k at + CH, v at + 2 CH
 
-    auto load_tile = [&](unsigned char* dst, const __half* src, uint32_t row0) {  // 64 rows x CH halves
-        for (int i = tid; i < kFaBN * kVec; i += kFaThreads) {
+    auto load_tile = [&](unsigned char* dst, const __half* src, uint32_t row0, int rows) {  // rows x CH halves
+        for (int i = tid; i < rows * kVec; i += kFaThreads) {
             const int r = i / kVec, v = i - r * kVec;
             fa_cp_async16((uint32_t)__cvta_generic_to_shared(dst + r * kRow + v * 16), src + (size_t)(row0 + r) * c3 + v * 8);
         }
     };
-    load_tile(sQ, base, q0);
-    load_tile(sK, base + CH, 0);
-    load_tile(sV, base + 2 * CH, 0);
+    load_tile(sQ, base, q0, kFaBM);
+    load_tile(sK, base + CH, 0, kFaBN);
+    load_tile(sV, base + 2 * CH, 0, kFaBN);
     fa_commit();
 
     uint32_t qf[kKC][4];
@@ -76,8 +79,8 @@ __global__ void __launch_bounds__(kFaThreads) k_flash_attn(const __half* __restr
     for (uint32_t j = 0; j < n_tiles; ++j) {
         const int buf = j & 1;
         if (j + 1 < n_tiles) {                                              // prefetch the next K / V tile into the other buffer
-            load_tile(sK + (buf ^ 1) * kTile, base + CH, (j + 1) * kFaBN);
-            load_tile(sV + (buf ^ 1) * kTile, base + 2 * CH, (j + 1) * kFaBN);
+            load_tile(sK + (buf ^ 1) * kTile, base + CH, (j + 1) * kFaBN, kFaBN);
+            load_tile(sV + (buf ^ 1) * kTile, base + 2 * CH, (j + 1) * kFaBN, kFaBN);
             fa_commit();
             fa_wait<1>();
         } else {
@@ -154,15 +157,15 @@ __global__ void __launch_bounds__(kFaThreads) k_flash_attn(const __half* __restr
     }
 }
 
-template <int CH>
+template <int CH, int WARPS>
 static int launch_flash(const __half* qkv, uint32_t B, uint32_t T, uint32_t heads, float scale, __half* out, cudaStream_t stream) {
-    constexpr size_t smem = 5 * (size_t)kFaBN * (CH * 2 + 16);
+    constexpr size_t smem = (size_t)(WARPS * 16 + 4 * kFaBN) * (CH * 2 + 16);
     static bool attr = false;
     if (!attr) {
-        SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_flash_attn<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_flash_attn<CH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    SSDNERF_CUDA_OK(launch_pdl(k_flash_attn<CH>, dim3(T / kFaBM, B * heads), dim3(kFaThreads), smem, stream, qkv, T, heads,
+    SSDNERF_CUDA_OK(launch_pdl(k_flash_attn<CH, WARPS>, dim3(T / (WARPS * 16), B * heads), dim3(WARPS * 32), smem, stream, qkv, T, heads,
                                scale * 1.4426950408889634f, out));
     SSDNERF_LAUNCH_OK();
     return 0;
@@ -177,7 +180,13 @@ extern "C" int ssdnerf_flash_attn(const void* qkv, uint32_t B, uint32_t T, uint3
     if (!qkv || !out) return set_error_msg(SSDNERF_ERR_ARG, "flash_attn: NULL buffer");
     if (T % 64) return set_error_msg(SSDNERF_ERR_ARG, "flash_attn: T must be a multiple of 64");
     if (((uintptr_t)qkv & 15u) || ((uintptr_t)out & 3u)) return set_error_msg(SSDNERF_ERR_ARG, "flash_attn: qkv must be 16-byte aligned");
-    if (ch == 64) return launch_flash<64>((const __half*)qkv, B, T, heads, scale, (__half*)out, (cudaStream_t)stream);
-    if (ch == 128) return launch_flash<128>((const __half*)qkv, B, T, heads, scale, (__half*)out, (cudaStream_t)stream);
+    // 128 queries per CTA (8 warps) when the sequence is long enough to still fill the GPU, else 64 (SSDNERF_FA_WARPS=4|8 overrides)
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("SSDNERF_FA_WARPS"); force = e ? atoi(e) : 0; }
+    const bool wide = force == 8 && T % 128 == 0;      // measured on B200 (T = 1024, ch = 64, 64 heads): 8 warps 86 us, 4 warps 75 us -> 4 is the default
+    if (ch == 64) return wide ? launch_flash<64, 8>((const __half*)qkv, B, T, heads, scale, (__half*)out, (cudaStream_t)stream)
+                              : launch_flash<64, 4>((const __half*)qkv, B, T, heads, scale, (__half*)out, (cudaStream_t)stream);
+    if (ch == 128) return wide ? launch_flash<128, 8>((const __half*)qkv, B, T, heads, scale, (__half*)out, (cudaStream_t)stream)
+                               : launch_flash<128, 4>((const __half*)qkv, B, T, heads, scale, (__half*)out, (cudaStream_t)stream);
     return set_error_msg(SSDNERF_ERR_ARG, "flash_attn: head width must be 64 or 128 channels");
 }

@@ -26,7 +26,7 @@ constexpr int kRwABox = 2 * 130 * 128;                  // bytes of one activati
 constexpr int kRwASlot = 33 * 1024;                     // slot stride (1024-aligned)
 constexpr int kRwBSlot = kRwN * 128;                    // 16 KB weight tile
 constexpr int kRwAStages = 2, kRwBStages = 7;
-constexpr size_t kRwSmem = (size_t)kRwAStages * kRwASlot + (size_t)kRwBStages * kRwBSlot + 1024 /*align*/ + 256 /*barriers*/ + 512 /*qacc*/ + 512 /*bias*/;
+constexpr size_t kRwSmem = (size_t)kRwAStages * kRwASlot + (size_t)kRwBStages * kRwBSlot + 1024 /*align*/ + 256 /*barriers*/ + 512 /*qacc*/ + 512 /*bias*/ + 8 * 2048 /*epilogue staging*/;
 
 struct ConvRowParams {
     uint32_t B, H;                // images, rows (H even)
@@ -54,6 +54,7 @@ k_conv_row2(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* qacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fullA) + 256);      // [32 quads][2]
     float* sbias = qacc + 128;                                                             // [128]
+    uint8_t* sstage = reinterpret_cast<uint8_t*>(sbias + 128);                              // [8 warps][32 rows][64 B]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_per_img = p.H / 2, total_tiles = p.B * tiles_per_img;
@@ -141,23 +142,44 @@ k_conv_row2(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const uint32_t b = tile / tiles_per_img, y0 = (tile - b * tiles_per_img) * 2;
-            const size_t off0 = (((size_t)b * p.H + y0) * kRwW + x) * kRwN + hsel * 64;
-            uint4 rcur[4], rnext[4];
-            auto fetch_res = [&](size_t off, uint4* r) {
+            // global accesses re-mapped through a per-warp staging tile: one warp instruction = 8 pixels x 64 contiguous bytes (see gemm_tc.cu)
+            const uint32_t wst = smem_u32(sstage) + (uint32_t)(warp - 2) * 2048u;     // shared-space address of this warp's staging tile
+            const uint32_t pc = (uint32_t)lane & 3u;
+            uint32_t st_own[4], st_map[4];     // swizzled byte offsets: own row (lane) piece g / re-mapped row (lane >> 2) + 8 i piece pc
 #pragma unroll
-                for (int g = 0; g < 4; ++g) r[g] = p.residual ? __ldg(reinterpret_cast<const uint4*>(p.residual + off) + g) : make_uint4(0, 0, 0, 0);
+            for (int g = 0; g < 4; ++g) {
+                st_own[g] = wst + (uint32_t)lane * 64u + (((uint32_t)g ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                const uint32_t r = ((uint32_t)lane >> 2) + 8u * g;
+                st_map[g] = wst + r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
+            }
+            const size_t offq = (((size_t)b * p.H + y0) * kRwW + q * 32) * kRwN + hsel * 64;      // pixel q*32 of row y0, this warp's column half
+            uint4 rcur[4], rnext[4];
+            auto fetch_res = [&](size_t off, uint4* r) {      // off: element offset of pixel q*32 for the wanted (row, chunk)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    r[i] = p.residual ? __ldg(reinterpret_cast<const uint4*>(p.residual + off + (size_t)(((uint32_t)lane >> 2) + 8u * i) * kRwN + pc * 8))
+                                      : make_uint4(0, 0, 0, 0);
             };
-            fetch_res(off0, rcur);
+            fetch_res(offq, rcur);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll
             for (int it = 0; it < 4; ++it) {                  // (row a, 32-column chunk ci)
                 const uint32_t a = it >> 1, ci = it & 1;
                 const uint32_t c0 = hsel * 64 + ci * 32;
-                const size_t off = off0 + (size_t)a * kRwW * kRwN + ci * 32;
+                const size_t off = offq + (size_t)a * kRwW * kRwN + ci * 32;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((q * 32u) << 16) + acc * 256 + a * kRwN + c0, v);
-                if (it + 1 < 4) fetch_res(off0 + (size_t)((it + 1) >> 1) * kRwW * kRwN + ((it + 1) & 1) * 32, rnext);
+                if (it + 1 < 4) fetch_res(offq + (size_t)((it + 1) >> 1) * kRwW * kRwN + ((it + 1) & 1) * 32, rnext);
+                uint4 rrow[4];
+                if (p.residual) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sts128(st_map[i], rcur[i]);
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) rrow[g] = lds128(st_own[g]);
+                    __syncwarp();
+                }
                 tmem_ld_wait();
                 float f[32];
 #pragma unroll
@@ -169,20 +191,26 @@ k_conv_row2(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
                 if (p.residual) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[g]);
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&rrow[g]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h2[i]); f[8 * g + 2 * i] += t.x; f[8 * g + 2 * i + 1] += t.y; }
                     }
                 }
-                __half* op = p.out + off;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 o;
                     __half2* h2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[8 * g + 2 * i], f[8 * g + 2 * i + 1]);
-                    reinterpret_cast<uint4*>(op)[g] = o;
+                    sts128(st_own[g], o);
                 }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t r = ((uint32_t)lane >> 2) + 8u * i;
+                    *reinterpret_cast<uint4*>(p.out + off + (size_t)r * kRwN + pc * 8) = lds128(st_map[i]);
+                }
+                __syncwarp();
                 if (p.qstats) {   // fused GroupNorm quad statistics (same reduce-scatter as gemm_tc.cu)
                     float sv[16];
 #pragma unroll

@@ -63,7 +63,7 @@ struct GemmCfg {
     static constexpr uint32_t kTxBytes = (kPair ? 2u : 1u) * kStageBytes;   // bytes credited to the (pair: leader's) full barrier per stage
     static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN in {32,64,128,256}
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*quad-stat accumulators*/ +
-                                    kMaxBiasN * 4 /*bias*/;
+                                    kMaxBiasN * 4 /*bias*/ + 8 * 2048 /*epilogue transpose staging, 2 KB per warp*/;
 };
 
 // The large layers are bound by the chip-wide L2 -> SM operand bandwidth (~60 B/clk/SM when all SMs pull; profiles/r01_gemm_pipeline_*),
@@ -90,6 +90,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* qacc = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [2 images][BN/4][2]
     float* sbias = qacc + 256;                                                               // [kMaxBiasN]
+    uint8_t* sstage = reinterpret_cast<uint8_t*>(sbias + kMaxBiasN);                          // [8 warps][32 rows][64 B]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
@@ -217,12 +218,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
             const uint32_t img0 = p.stats_hw ? (t1 * p.b1) / p.stats_hw : t3 * p.b3;
             const uint32_t slot = (img - img0) & 1u;
             const uint32_t cbeg = hsel * (BN / 2);
+            // Global accesses of the epilogue are re-mapped through a 2 KB per-warp staging tile so that one warp instruction touches
+            // 8 rows x 64 contiguous bytes (4 lanes per row) instead of 32 rows x 16 bytes: a row-per-lane 16-byte access costs 32 LSU
+            // wavefronts and made every short-K GEMM epilogue-bound (~2.7 k cycles per 32-column chunk, profiles/r01_gemm_pipeline_prof.txt).
+            const uint32_t wst = smem_u32(sstage) + (uint32_t)(warp - 2) * 2048u;     // shared-space address of this warp's staging tile
+            const uint32_t pc = (uint32_t)lane & 3u;
+            uint32_t st_own[4], st_map[4];     // swizzled byte offsets: own row (lane) piece g / re-mapped row (lane >> 2) + 8 i piece pc
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                st_own[g] = wst + (uint32_t)lane * 64u + (((uint32_t)g ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                const uint32_t r = ((uint32_t)lane >> 2) + 8u * g;
+                st_map[g] = wst + r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
+            }
+            long long roff[4]; bool rok[4];            // rows (lane >> 2) + 8 i of this warp's 32-row slice, as seen by the re-mapped accesses
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t rr = q * 32 + ((uint32_t)lane >> 2) + 8u * i;
+                const uint32_t j1 = rr % p.b1, j2 = (rr / p.b1) % p.b2, j3 = rr / (p.b1 * p.b2);
+                const uint32_t h1 = t1 * p.b1 + j1, h2 = t2 * p.b2 + j2, h3 = t3 * p.b3 + j3;
+                rok[i] = m_tile < tiles_m && h1 < p.d1 && h2 < p.d2 && h3 < p.d3;
+                roff[i] = (long long)h1 * p.so1 + (long long)h2 * p.so2 + (long long)h3 * p.so3 + (long long)n_tile * BN;
+            }
             // the residual does not depend on the accumulator: its loads are issued before the wait on the MMA (and one chunk ahead)
             uint4 rcur[4], rnext[4];
             auto fetch_res = [&](uint32_t c0, uint4* r) {
-                const bool ok = p.residual && row_ok && (n_tile * BN + c0 + 32 <= p.n_valid);
+                const bool full = p.residual && (n_tile * BN + c0 + 32 <= p.n_valid);          // warp-uniform
 #pragma unroll
-                for (int g = 0; g < 4; ++g) r[g] = ok ? __ldg(reinterpret_cast<const uint4*>(p.residual + off + c0) + g) : make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < 4; ++i)
+                    r[i] = (full && rok[i]) ? __ldg(reinterpret_cast<const uint4*>(p.residual + roff[i] + c0 + pc * 8)) : make_uint4(0, 0, 0, 0);
             };
             fetch_res(cbeg, rcur);
             if (p.prof) { const long long c = clock64(); mbar_wait(&tfull[acc], acc_phase); ew += clock64() - c; }
@@ -234,16 +257,28 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((q * 32u) << 16) + acc * BN + c0, v);
                 if (ci + 1 < kChunks) fetch_res(c0 + 32, rnext);
-                tmem_ld_wait();
                 const uint32_t ncol0 = n_tile * BN + c0;
-                float f[32];
+                const bool full32 = (ncol0 + 32 <= p.n_valid);                                  // warp-uniform
+                uint4 rrow[4];                                                                  // this lane's own row of the residual
+                if (p.residual && full32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = 0.0f;
-                const bool live = row_ok && ncol0 < p.n_valid;
-                if (live) {
-                    const bool full32 = (ncol0 + 32 <= p.n_valid);
+                    for (int i = 0; i < 4; ++i) sts128(st_map[i], rcur[i]);
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) rrow[g] = lds128(st_own[g]);
+                    __syncwarp();
+                }
+                tmem_ld_wait();
+                float f[32];
+                const bool live = row_ok && ncol0 < p.n_valid;      // rows / columns outside the problem: f is never stored and masked out of the statistics
+                if (p.alpha != 1.0f) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                }
+                if (live) {
                     if (has_bias) {
                         if (full32) {
 #pragma unroll
@@ -260,7 +295,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                         if (full32) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[g]);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rrow[g]);
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h2[i]); f[8 * g + 2 * i] += t.x; f[8 * g + 2 * i + 1] += t.y; }
                             }
@@ -269,6 +304,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                             for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) f[i] += __half2float(rp[i]);
                         }
                     }
+                }
+                if (!p.out_f32 && full32) {          // fp16 rows through the staging tile (warp-uniform branch)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 o;
+                        __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[8 * g + 2 * i], f[8 * g + 2 * i + 1]);
+                        sts128(st_own[g], o);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 o = lds128(st_map[i]);
+                        if (rok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + roff[i] + c0 + pc * 8) = o;
+                    }
+                    __syncwarp();
+                } else if (live) {
                     if (p.out_f32) {
                         float* op = reinterpret_cast<float*>(p.out) + off + c0;
                         if (full32) {
@@ -279,18 +332,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                         }
                     } else {
                         __half* op = reinterpret_cast<__half*>(p.out) + off + c0;
-                        if (full32) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                uint4 o;
-                                __half2* h2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[8 * g + 2 * i], f[8 * g + 2 * i + 1]);
-                                reinterpret_cast<uint4*>(op)[g] = o;
-                            }
-                        } else {
-                            for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) op[i] = __float2half_rn(f[i]);
-                        }
+                        for (int i = 0; i < 32; ++i) if (ncol0 + i < p.n_valid) op[i] = __float2half_rn(f[i]);
                     }
                 }
                 if (p.qstats) {   // fused GroupNorm statistics of the fp32 output values: 8 quads x {sum, sumsq} per thread ...
