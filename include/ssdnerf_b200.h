@@ -276,6 +276,28 @@ SSDNERF_API int ssdnerf_gn_apply(const void* x1, uint32_t C1, const void* x2, ui
 SSDNERF_API int ssdnerf_im2col_s2(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream);
 /* nearest-neighbour x2 (DenoisingUpsample) */
 SSDNERF_API int ssdnerf_upsample2x(const void* x, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* out, void* stream);
+/* Fused GroupNorm(32) (+ NormWithEmbedding scale/shift) + SiLU + 3x3 convolution, 128-pixel-wide images, 128 output channels
+ * (the UNet's 128 x 128 level).  replaces: mmgen DenoisingResBlock's `conv(act(norm(x)))` pairs as used by
+ * lib/models/architecture/ddpm/modules.py:51-110 -- GroupNorm apply + SiLU + Conv2d, without materialising the normalised activation.
+ * x1 (+ x2, channel concat) are the RAW NHWC fp16 tensors; q1 / q2 their quad statistics as emitted by ssdnerf_gemm_f16 (qstats). */
+typedef struct ssdnerf_conv_gn_args {
+    const void* x1; uint32_t C1;          /* [B][H][128][C1] fp16 */
+    const void* x2; uint32_t C2;          /* optional second input [B][H][128][C2] */
+    uint32_t B, H;                         /* H even */
+    const float* q1; const float* q2;      /* [B][C/4][2] */
+    const float* gamma; const float* beta; /* [C1 + C2] */
+    const float* scale_shift;              /* optional [B][...]: row b holds scale[C] | shift[C] at scale_shift + b * ss_batch_stride */
+    long long ss_batch_stride;
+    float eps;
+    const void* w; uint32_t w_rows;        /* packed fp16 weight [9][w_rows >= 128][C1 + C2] */
+    const float* bias;                     /* [128] or NULL */
+    const void* residual;                  /* [B][H][128][128] fp16 or NULL */
+    void* out;                             /* [B][H][128][128] fp16 */
+    float* qstats;                         /* optional [B][32][2] quad statistics of the output (caller zero-fills) */
+    void* coef_workspace;                  /* device scratch, B * (C1 + C2) * 8 bytes, 16-byte aligned (per-image affine table) */
+    void* debug_cycles;                    /* optional uint64[8] pipeline wait counters (debug); NULL in production */
+} ssdnerf_conv_gn_args;
+SSDNERF_API int ssdnerf_conv3x3_gn_f16(const ssdnerf_conv_gn_args* args, void* stream);
 /* fused attention: out[b][t][h*ch + d] = softmax_s(scale * q[b,t,h,:] . k[b,s,h,:]) v[b,s,h,d], scores kept on chip (flash-style);
  * qkv fp16 [B][T][3*heads*ch] with the legacy head layout (modules.py:36-48), ch in {64, 128}, T % 64 == 0 */
 SSDNERF_API int ssdnerf_flash_attn(const void* qkv, uint32_t B, uint32_t T, uint32_t heads, uint32_t ch, float scale, void* out, void* stream);

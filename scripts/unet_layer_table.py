@@ -43,7 +43,7 @@ else:
         L.append((d['Kernel Name'], d['Grid Size'], v / 1e3))
     idx = max(i for i, x in enumerate(L) if 'k_nchw_to_nhwc' in x[0])
     ev = L[idx:]
-    gem = [x for x in ev if 'k_gemm_tc' in x[0] or 'k_conv_row2' in x[0]]
+    gem = [x for x in ev if 'k_gemm_tc' in x[0] or 'k_conv_row2' in x[0]]      # k_conv_row2 and k_conv_row2_gn (fused GroupNorm + SiLU)
     assert len(gem) == len(log), (len(gem), len(log))
     tot = sum(v for _, _, v in ev)
     print(f'one UNet evaluation (B=16), warm per-kernel durations: {tot:.1f} us over {len(ev)} launches; GEMM launches: {len(gem)}')
@@ -56,7 +56,7 @@ else:
         print(f'  glue {k:34s} {v[0]:4d} launches {v[1]:9.1f} us')
     agg = {}
     for (k, g, v), a in zip(gem, log):
-        key = (a['M'], a['N'], a['K'] * a['taps'], a['taps'], a['batched'], k.split('<')[1].split('>')[0] if '<' in k else 'row2', g)
+        key = (a['M'], a['N'], a['K'] * a['taps'], a['taps'], a['batched'], ('gn+row2' if 'row2_gn' in k else (k.split('<')[1].split('>')[0] if 'k_gemm_tc' in k else 'row2')), g)
         e = agg.setdefault(key, [0, 0.0]); e[0] += 1; e[1] += v
     print(f'{"M":>8} {"N":>5} {"Ktot":>6} taps bat  tile<BN,CL> grid        n    us/launch  TFLOP/s   total us  lost-vs-1.3PF us')
     tl = 0

@@ -14,6 +14,7 @@
 // (bias, residual, fp16 store, fused GroupNorm quad statistics).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "conv_row_epilogue.cuh"
 #include "../../include/ssdnerf_b200.h"
 #include <cuda_fp16.h>
 
@@ -21,7 +22,6 @@ namespace ssdnerf {
 using namespace tc;
 
 constexpr int kRwThreads = 320, kRwEpi = 256;
-constexpr int kRwW = 128, kRwN = 128;                   // image width (pixels per row) and output channels
 constexpr int kRwABox = 2 * 130 * 128;                  // bytes of one activation box: 2 rows x 130 pixels x 64 halves
 constexpr int kRwASlot = 33 * 1024;                     // slot stride (1024-aligned)
 constexpr int kRwBSlot = kRwN * 128;                    // 16 KB weight tile
@@ -136,125 +136,9 @@ k_conv_row2(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ C
         }
         if (p.prof && lane == 0) { atomicAdd(p.prof + 2, (unsigned long long)wf); atomicAdd(p.prof + 4, (unsigned long long)(clock64() - mt0)); }
         __syncwarp();
-    } else {   // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4 (pixels), column half = (warp - 2) / 4
-        const uint32_t q = (uint32_t)warp & 3u, hsel = (uint32_t)(warp - 2) >> 2;
-        const uint32_t x = q * 32 + (uint32_t)lane;
-        uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const uint32_t b = tile / tiles_per_img, y0 = (tile - b * tiles_per_img) * 2;
-            // global accesses re-mapped through a per-warp staging tile: one warp instruction = 8 pixels x 64 contiguous bytes (see gemm_tc.cu)
-            const uint32_t wst = smem_u32(sstage) + (uint32_t)(warp - 2) * 2048u;     // shared-space address of this warp's staging tile
-            const uint32_t pc = (uint32_t)lane & 3u;
-            uint32_t st_own[4], st_map[4];     // swizzled byte offsets: own row (lane) piece g / re-mapped row (lane >> 2) + 8 i piece pc
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                st_own[g] = wst + (uint32_t)lane * 64u + (((uint32_t)g ^ (((uint32_t)lane >> 1) & 3u)) << 4);
-                const uint32_t r = ((uint32_t)lane >> 2) + 8u * g;
-                st_map[g] = wst + r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
-            }
-            const size_t offq = (((size_t)b * p.H + y0) * kRwW + q * 32) * kRwN + hsel * 64;      // pixel q*32 of row y0, this warp's column half
-            uint4 rcur[4], rnext[4];
-            auto fetch_res = [&](size_t off, uint4* r) {      // off: element offset of pixel q*32 for the wanted (row, chunk)
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    r[i] = p.residual ? __ldg(reinterpret_cast<const uint4*>(p.residual + off + (size_t)(((uint32_t)lane >> 2) + 8u * i) * kRwN + pc * 8))
-                                      : make_uint4(0, 0, 0, 0);
-            };
-            fetch_res(offq, rcur);
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {                  // (row a, 32-column chunk ci)
-                const uint32_t a = it >> 1, ci = it & 1;
-                const uint32_t c0 = hsel * 64 + ci * 32;
-                const size_t off = offq + (size_t)a * kRwW * kRwN + ci * 32;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((q * 32u) << 16) + acc * 256 + a * kRwN + c0, v);
-                if (it + 1 < 4) fetch_res(offq + (size_t)((it + 1) >> 1) * kRwW * kRwN + ((it + 1) & 1) * 32, rnext);
-                uint4 rrow[4];
-                if (p.residual) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) sts128(st_map[i], rcur[i]);
-                    __syncwarp();
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) rrow[g] = lds128(st_own[g]);
-                    __syncwarp();
-                }
-                tmem_ld_wait();
-                float f[32];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + 4 * g);
-                    f[4 * g] = __uint_as_float(v[4 * g]) + bv.x; f[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + bv.y;
-                    f[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + bv.z; f[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + bv.w;
-                }
-                if (p.residual) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const __half2* h2 = reinterpret_cast<const __half2*>(&rrow[g]);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h2[i]); f[8 * g + 2 * i] += t.x; f[8 * g + 2 * i + 1] += t.y; }
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 o;
-                    __half2* h2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[8 * g + 2 * i], f[8 * g + 2 * i + 1]);
-                    sts128(st_own[g], o);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t r = ((uint32_t)lane >> 2) + 8u * i;
-                    *reinterpret_cast<uint4*>(p.out + off + (size_t)r * kRwN + pc * 8) = lds128(st_map[i]);
-                }
-                __syncwarp();
-                if (p.qstats) {   // fused GroupNorm quad statistics (same reduce-scatter as gemm_tc.cu)
-                    float sv[16];
-#pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        float su = 0.0f, sq = 0.0f;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { const float xv = f[4 * q4 + e]; su += xv; sq = fmaf(xv, xv, sq); }
-                        sv[q4] = su; sv[8 + q4] = sq;
-                    }
-#pragma unroll
-                    for (int m = 16, half = 8; m >= 2; m >>= 1, half >>= 1) {
-                        const bool upper = (lane & m) != 0;
-#pragma unroll
-                        for (int i = 0; i < half; ++i) {
-                            const float send = upper ? sv[i] : sv[i + half];
-                            const float recv = __shfl_xor_sync(0xffffffffu, send, m);
-                            sv[i] = (upper ? sv[i + half] : sv[i]) + recv;
-                        }
-                    }
-                    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                    if ((lane & 1) == 0) {
-                        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(qacc + (c0 / 4 + (idx & 7)) * 2 + (idx >> 3), sv[0]);
-                    }
-                }
-                if (it + 1 < 4) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
-            if (p.qstats) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const uint32_t et = threadIdx.x - 64;
-                if (et < 64) {
-                    const float val = qacc[et];
-                    if (val != 0.0f) atomicAdd(p.qstats + (size_t)b * 64 + et, val);
-                    qacc[et] = 0.0f;
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
+    } else {   // ---------------- epilogue warps 2..9 (conv_row_epilogue.cuh)
+        const RowEpiArgs ea{p.H, p.residual, p.out, p.qstats};
+        conv_row_epilogue<8>(ea, warp, lane, total_tiles, tiles_per_img, tmem_base, tfull, tempty, sstage, sbias, qacc);
     }
     tc_fence_before();
     __syncthreads();

@@ -9,6 +9,7 @@ softmax and layout glue as fused memory-bound kernels.  Forward semantics of the
 mmgen 0.7.2 are restated per SURVEY.md Appendix B.  Inference only (no autograd through the engine).
 """
 import math
+import os
 from copy import deepcopy
 
 import torch
@@ -206,6 +207,7 @@ class UNetEngine:
     def __init__(self, m: DenoisingUnetMod, batch, device):
         self.m, self.B, self.dev = m, batch, torch.device(device)
         self.flash_attention = True      # False: unfused scores -> softmax -> PV composition (A/B tests)
+        self.fused_gn_conv = os.environ.get('SSDNERF_FUSED_GN_CONV', '1') != '0'   # 128x128-level resblocks: GN + SiLU inside the conv kernel
         self.H, self.W = m.image_size
         self.bufs = {}
         self.cin_total = m.in_channels + m.concat_cond_channels
@@ -327,15 +329,24 @@ class UNetEngine:
         (x, qx), (sk, qs) = x, (skip if skip is not None else (None, None))
         B, H, W, _ = x.shape
         cin, cout = d['cin'], d['cout']
-        a = self._gn(x, qx, sk, qs, d['g1'], d['b1'], self._buf(('a', H, cin), (B, H, W, cin)), True)
-        qh1 = self._q(('h1', tag), cout)
-        h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', H, cout), (B, H, W, cout)), qstats=qh1)
-        a2 = self._gn(h1, qh1, None, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
         if 'ws' in d:
             sc = U.conv3x3_f16(x, d['ws'].unsqueeze(0), cout, bias=d['wsb'], x2=sk, taps=1, out=self._buf(('sc', H, cout), (B, H, W, cout)))
         else:
             sc = x
+        qh1 = self._q(('h1', tag), cout)
         qo = self._q(('res_out', tag), cout)
+        if self.fused_gn_conv and W == 128 and cout == 128 and cin <= 384 and (cin // 32) % 4 == 0:
+            # 128 x 128 level: GroupNorm apply + SiLU ride on the convolution's activation load path (csrc/conv_row2_gn.cu)
+            h1 = U.conv3x3_gn_f16(x, qx, d['g1'], d['b1'], d['w1'], bias=d['c1b'], x2=sk, q2=qs,
+                                  out=self._buf(('h1', H, cout), (B, H, W, cout)), qstats=qh1,
+                                  coef_ws=self._buf(('gncoef', 1, tag), (B * cin * 2,), torch.float32))
+            ss = N.c_void_p(self.ss_cur.data_ptr() + 4 * self.ss_offsets[d['idx']])
+            return U.conv3x3_gn_f16(h1, qh1, d['g2'], d['b2'], d['w2'], bias=d['c2b'], scale_shift_ptr=ss, ss_batch_stride=self.ss_total,
+                                    residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)), qstats=qo,
+                                    coef_ws=self._buf(('gncoef', 2, tag), (B * cout * 2,), torch.float32)), qo
+        a = self._gn(x, qx, sk, qs, d['g1'], d['b1'], self._buf(('a', H, cin), (B, H, W, cin)), True)
+        h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', H, cout), (B, H, W, cout)), qstats=qh1)
+        a2 = self._gn(h1, qh1, None, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
         return U.conv3x3_f16(a2, d['w2'], cout, bias=d['c2b'], residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)), qstats=qo), qo
 
     def _attn(self, d, x, tag):

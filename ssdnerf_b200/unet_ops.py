@@ -192,3 +192,47 @@ def flash_attn(qkv, heads, scale, out=None):
     N.check(N.lib().ssdnerf_flash_attn(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.c_f32(scale), N.ptr(out),
                                        N.stream_ptr()))
     return out
+
+
+class ConvGnArgs(ctypes.Structure):
+    """mirror of `ssdnerf_conv_gn_args`"""
+    _fields_ = [
+        ('x1', N.c_void_p), ('C1', N.c_u32), ('x2', N.c_void_p), ('C2', N.c_u32), ('B', N.c_u32), ('H', N.c_u32),
+        ('q1', N.c_void_p), ('q2', N.c_void_p), ('gamma', N.c_void_p), ('beta', N.c_void_p), ('scale_shift', N.c_void_p),
+        ('ss_batch_stride', c_ll), ('eps', N.c_f32), ('w', N.c_void_p), ('w_rows', N.c_u32), ('bias', N.c_void_p),
+        ('residual', N.c_void_p), ('out', N.c_void_p), ('qstats', N.c_void_p), ('coef_workspace', N.c_void_p), ('debug_cycles', N.c_void_p),
+    ]
+
+
+def conv3x3_gn_f16(x1, q1, gamma, beta, wp, bias=None, x2=None, q2=None, scale_shift_ptr=None, ss_batch_stride=0, eps=1e-5,
+                   residual=None, out=None, qstats=None, coef_ws=None):
+    """out = conv3x3(SiLU(GroupNorm32(cat(x1, x2)) * (1 + scale) + shift)) + bias + residual on RAW inputs (csrc/conv_row2_gn.cu).
+    x1 / x2 NHWC fp16 [B,H,128,C]; q1 / q2 their quad statistics; wp packed weight [9][rows][C1+C2]; 128 output channels."""
+    N.require_cuda(x1, wp, q1)
+    B, H, W, C1 = x1.shape
+    assert W == 128 and x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    if out is None:
+        out = torch.empty(B, H, W, 128, dtype=torch.float16, device=x1.device)
+    a = ConvGnArgs()
+    a.x1, a.C1 = x1.data_ptr(), C1
+    if x2 is not None:
+        a.x2, a.C2, a.q2 = x2.data_ptr(), x2.shape[-1], q2.data_ptr()
+    a.B, a.H = B, H
+    a.q1, a.gamma, a.beta = q1.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    if scale_shift_ptr is not None:
+        a.scale_shift, a.ss_batch_stride = scale_shift_ptr, ss_batch_stride
+    a.eps = eps
+    a.w, a.w_rows = wp.data_ptr(), wp.shape[-2]
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.out = out.data_ptr()
+    a.qstats = qstats.data_ptr() if qstats is not None else None
+    if coef_ws is None:
+        coef_ws = torch.empty(B * (C1 + (x2.shape[-1] if x2 is not None else 0)) * 2, dtype=torch.float32, device=x1.device)
+    a.coef_workspace = coef_ws.data_ptr()
+    if GEMM_PROF is not None:
+        a.debug_cycles = GEMM_PROF.data_ptr()
+    if GEMM_LOG is not None:
+        GEMM_LOG.append(dict(M=B * H * W, N=128, K=int(a.C1) + int(a.C2), taps=9, bn=128, cluster=1, batched=0, qstats=bool(a.qstats), f32=0, fused_gn=True))
+    N.check(N.lib().ssdnerf_conv3x3_gn_f16(ctypes.byref(a), N.stream_ptr()))
+    return out

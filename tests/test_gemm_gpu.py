@@ -117,3 +117,52 @@ def test_conv3x3_row_pair_kernel(cuda, B, H, C1, C2):
     _check(outs[1], ref)
     torch.testing.assert_close(outs[2].float(), outs[1].float(), rtol=2e-3, atol=2e-3)
     torch.testing.assert_close(stats[2], stats[1], rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize('B,H,C1,C2,use_ss', [(2, 8, 128, 0, False), (1, 128, 128, 0, True), (3, 6, 128, 128, False), (2, 4, 256, 128, True)])
+def test_fused_groupnorm_silu_conv(cuda, B, H, C1, C2, use_ss):
+    """GroupNorm(32) (+ scale/shift) + SiLU + conv3x3 on RAW inputs in one kernel vs the gn_apply pass followed by the convolution kernels
+    and vs fp32 PyTorch GroupNorm -> SiLU -> conv2d.  The fused kernel evaluates SiLU on packed halves (tanh.approx.f16x2): its normalised
+    activation is within ~2 fp16 ulps of the two-pass one, so outputs (sums over 1152-3456 terms) agree to ~1e-3 of the output range."""
+    from ssdnerf_b200 import _lib as N
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + C1 + C2 + int(use_ss))
+    W, Cout, C = 128, 128, C1 + C2
+    x1 = (torch.randn(B, H, W, C1, generator=g) * 1.5 + 0.3).half().to(cuda)
+    x2 = (torch.randn(B, H, W, C2, generator=g) * 0.7 - 0.2).half().to(cuda) if C2 else None
+
+    def quads(x):
+        xf = x.float().view(x.shape[0], -1, x.shape[-1] // 4, 4)
+        return torch.stack([xf.sum(dim=(1, 3)), (xf * xf).sum(dim=(1, 3))], dim=-1).contiguous()
+    q1, q2 = quads(x1), (quads(x2) if C2 else None)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(cuda)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda)
+    ss = (0.3 * torch.randn(B, 2 * C + 64, generator=g)).to(cuda) if use_ss else None      # row b: [pad 64][scale C][shift C]
+    ss_ptr = N.c_void_p(ss.data_ptr() + 4 * 64) if use_ss else None
+    w = torch.randn(Cout, C, 3, 3, generator=g) * 0.05
+    wp = U.pack_conv_weight(w).to(cuda)
+    wp = torch.cat([wp, wp.new_zeros(9, max(0, 128 - wp.shape[1]), C)], dim=1).contiguous()
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    res = torch.randn(B, H, W, Cout, generator=g).half().to(cuda)
+    qf = torch.zeros(B, Cout // 4, 2, device=cuda)
+    out = U.conv3x3_gn_f16(x1, q1, gamma, beta, wp, bias=bias, x2=x2, q2=q2, scale_shift_ptr=ss_ptr, ss_batch_stride=ss.shape[1] if use_ss else 0,
+                           residual=res, qstats=qf)
+    # two-pass composition of this library
+    y = torch.empty(B, H, W, C, dtype=torch.float16, device=cuda)
+    N.check(N.lib().ssdnerf_gn_apply_q(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(q1), N.ptr(q2),
+                                       N.ptr(gamma), N.ptr(beta), ss_ptr, N.c_longlong(ss.shape[1] if use_ss else 0), N.c_f32(1e-5), N.c_int(1),
+                                       N.ptr(y), N.stream_ptr()))
+    q2p = torch.zeros(B, Cout // 4, 2, device=cuda)
+    ref2 = U.conv3x3_f16(y, wp, Cout, bias=bias, residual=res, qstats=q2p, algo=1)
+    scale = ref2.float().abs().max().item()
+    e2 = (out.float() - ref2.float()).abs().max().item() / scale
+    eq = ((qf - q2p).abs() / (q2p.abs() + 0.05 * q2p.abs().max())).max().item()
+    print(f'fused vs two-pass: max err {e2:.2e} of range, quad stats rel {eq:.2e}')
+    assert e2 < 3e-3 and eq < 2e-2
+    # fp32 reference
+    xin = torch.cat([x1, x2], dim=-1) if C2 else x1
+    xn = torch.nn.functional.group_norm(xin.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5)
+    if use_ss:
+        xn = xn * (1 + ss[:, 64:64 + C, None, None]) + ss[:, 64 + C:64 + 2 * C, None, None]
+    ref = torch.nn.functional.conv2d(torch.nn.functional.silu(xn), w.half().float().to(cuda), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref, tol=5e-3)
