@@ -35,9 +35,6 @@ struct SmemP2 {
     float bd, bc[3], sat;
 };
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {   // packed converts (F2FP), not 4 scalar F2F
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
