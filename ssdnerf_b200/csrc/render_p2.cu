@@ -223,9 +223,11 @@ __global__ void __launch_bounds__(kP2Threads, MINB) k_render_p2(RenderParams p, 
                 for (int j = 0; j < 4; ++j) {
                     const float2 df = *reinterpret_cast<const float2*>(dirw + (g + 8 * j) * kDirStride + col);
                     const float bx0 = d[j >> 1][(j & 1) * 2], bx1 = d[j >> 1][(j & 1) * 2 + 1];
-                    psd[j] = fmaf(silu_f(bx0), hw0.x, psd[j]);
-                    psd[j] = fmaf(silu_f(bx1), hw1.x, psd[j]);
-                    const float h0 = silu_f(bx0 + df.x), h1 = silu_f(bx1 + df.y);
+                    float s0, s1, h0, h1;
+                    silu_pair(bx0, bx1, s0, s1);
+                    silu_pair(bx0 + df.x, bx1 + df.y, h0, h1);
+                    psd[j] = fmaf(s0, hw0.x, psd[j]);
+                    psd[j] = fmaf(s1, hw1.x, psd[j]);
                     pr[j] = fmaf(h0, hw0.y, pr[j]); pg[j] = fmaf(h0, hw0.z, pg[j]); pb[j] = fmaf(h0, hw0.w, pb[j]);
                     pr[j] = fmaf(h1, hw1.y, pr[j]); pg[j] = fmaf(h1, hw1.z, pg[j]); pb[j] = fmaf(h1, hw1.w, pb[j]);
                 }
