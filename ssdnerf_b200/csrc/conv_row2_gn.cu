@@ -158,9 +158,12 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
         // coefficients one chunk ahead of the transform, across tile boundaries
         const uint32_t my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const uint32_t rpt = KC * 4u, n_rows = my_tiles * rpt;
-        auto issue_row = [&](uint32_t g, uint4* v) {                  // raw 16-byte chunks of stream row g for pixels p0 + 32 n (zero outside the image)
-            const uint32_t t = g / rpt, w = g - t * rpt, j = w >> 2, r = w & 3u;
-            const uint32_t tile = blockIdx.x + t * gridDim.x, b = tile / tiles_per_img, y0 = (tile - b * tiles_per_img) * 2;
+        // stream position = (tile, row-within-tile w = 4 j + r), advanced without divisions
+        struct Cur { uint32_t tile, w; };
+        auto advance = [&](Cur& c) { if (++c.w == rpt) { c.w = 0; c.tile += gridDim.x; } };
+        auto issue_row = [&](const Cur& c, uint4* v) {                // raw 16-byte chunks of the row for pixels p0 + 32 n (zero outside the image)
+            const uint32_t j = c.w >> 2, r = c.w & 3u;
+            const uint32_t b = c.tile / tiles_per_img, y0 = (c.tile - b * tiles_per_img) * 2;
             const bool first = j < kc1;
             const __half* src = first ? p.x1 : p.x2;
             const uint32_t Cs = first ? p.C1 : p.C2, cl = (first ? j : j - kc1) * 64u + c8 * 8u;
@@ -169,66 +172,68 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
             const __half* rowp = src + (((size_t)b * p.H + (row_ok ? y : 0)) * kRwW) * Cs + cl;
 #pragma unroll
             for (int n = 0; n < 5; ++n) {
-                const uint32_t px = p0 + 32u * n;
-                const int x = (int)px - 1;
-                v[n] = (row_ok && px < 130u && x >= 0 && x < kRwW) ? __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)x * Cs)) : make_uint4(0, 0, 0, 0);
+                const int x = (int)(p0 + 32u * n) - 1;
+                v[n] = (row_ok && (unsigned)x < (unsigned)kRwW) ? __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)x * Cs)) : make_uint4(0, 0, 0, 0);
             }
         };
-        auto issue_coef = [&](uint32_t g, float4* c) {                // {a, b} of this thread's 8 channels for the chunk stream row g belongs to
-            const uint32_t t = g / rpt, j = (g - t * rpt) >> 2;
-            const uint32_t tile = blockIdx.x + t * gridDim.x, b = tile / tiles_per_img;
-            const float4* cp = reinterpret_cast<const float4*>(p.coef + (size_t)b * C + j * 64u + c8 * 8u);
+        auto issue_coef = [&](const Cur& c, float4* cf) {             // {a, b} of this thread's 8 channels for the chunk the row belongs to
+            const uint32_t b = c.tile / tiles_per_img;
+            const float4* cp = reinterpret_cast<const float4*>(p.coef + (size_t)b * C + (c.w >> 2) * 64u + c8 * 8u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] = __ldg(cp + k);
+            for (int k = 0; k < 4; ++k) cf[k] = __ldg(cp + k);
         };
         uint4 vcur[5], vn1[5], vn2[5];
         float4 cn[4];
         float ca[8], cb[8];
-        if (n_rows) { issue_coef(0, cn); issue_row(0, vcur); issue_row(1, vn1); }
+        Cur cu{blockIdx.x, 0}, cl2{blockIdx.x, 0}, cc{blockIdx.x, 0};      // transform cursor, load cursor (2 rows ahead), coefficient cursor (next chunk)
+        if (n_rows) {
+            issue_coef(cc, cn);
+            issue_row(cl2, vcur); advance(cl2);
+            if (n_rows > 1) { issue_row(cl2, vn1); advance(cl2); }
+        }
         uint32_t rctr = 0;
         long long lw = 0; const long long l0 = clock64();
         for (uint32_t g = 0; g < n_rows; ++g) {
-            const uint32_t t = g / rpt, w = g - t * rpt, r = w & 3u;
-            const uint32_t tile = blockIdx.x + t * gridDim.x, b = tile / tiles_per_img, y0 = (tile - b * tiles_per_img) * 2;
+            const uint32_t r = cu.w & 3u;
+            const uint32_t b = cu.tile / tiles_per_img, y0 = (cu.tile - b * tiles_per_img) * 2;
             if (r == 0) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { ca[2 * k] = 0.5f * cn[k].x; cb[2 * k] = 0.5f * cn[k].y; ca[2 * k + 1] = 0.5f * cn[k].z; cb[2 * k + 1] = 0.5f * cn[k].w; }
+                cc = cu; cc.w += 3; advance(cc);                      // first row of the next chunk
             }
-            if (r == 1 && g + 3 < n_rows) issue_coef(g + 3, cn);
-            if (g + 2 < n_rows) issue_row(g + 2, vn2);
+            if (r == 1 && g + 3 < n_rows) issue_coef(cc, cn);
+            if (g + 2 < n_rows) { issue_row(cl2, vn2); advance(cl2); }
             const uint32_t slot = rctr % kGnRowSlots, ph = (rctr / kGnRowSlots) & 1u;
             if (p.prof) { const long long c_ = clock64(); mbar_wait(&emptyR[slot], ph ^ 1); lw += clock64() - c_; } else mbar_wait(&emptyR[slot], ph ^ 1);
             const int y = (int)(y0 + r) - 1;
             const bool row_ok = y >= 0 && y < (int)p.H;
             const uint32_t dst = smem_u32(sR + slot * kGnRowSlot);
+            // branch-free transform of the 5 chunks (independent dependency chains the scheduler can interleave); padding pixels are forced to zero
 #pragma unroll
             for (int n = 0; n < 5; ++n) {
                 const uint32_t px = p0 + 32u * n;
-                const int x = (int)px - 1;
-                if (px < 130u) {
-                    uint4 o = make_uint4(0, 0, 0, 0);
-                    if (row_ok && x >= 0 && x < kRwW) {
-                        const __half2* h = reinterpret_cast<const __half2*>(&vcur[n]);
-                        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+                const bool ok = row_ok && (unsigned)((int)px - 1) < (unsigned)kRwW;
+                const __half2* h = reinterpret_cast<const __half2*>(&vcur[n]);
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            // affine in fp32 (half of it: ca / cb carry the factor 0.5), SiLU(u) = h + h tanh(h) with h = u / 2 on packed halves:
-                            // one MUFU per two elements instead of four; result within 2 fp16 ulps of the fp32 evaluation of k_gn_apply
-                            const float2 tt = __half22float2(h[k]);
-                            const __half2 hh = __floats2half2_rn(fmaf(tt.x, ca[2 * k], cb[2 * k]), fmaf(tt.y, ca[2 * k + 1], cb[2 * k + 1]));
-                            uint32_t hv = *reinterpret_cast<const uint32_t*>(&hh), tv;
-                            asm("tanh.approx.f16x2 %0, %1;" : "=r"(tv) : "r"(hv));
-                            const __half2 yy = __hfma2(hh, *reinterpret_cast<const __half2*>(&tv), hh);
-                            ow[k] = *reinterpret_cast<const uint32_t*>(&yy);
-                        }
-                    }
-                    sts128(dst + px * 128u + ((c8 ^ (px & 7u)) << 4), o);
+                for (int k = 0; k < 4; ++k) {
+                    // affine in fp32 (half of it: ca / cb carry the factor 0.5), SiLU(u) = h + h tanh(h) with h = u / 2 on packed halves:
+                    // one MUFU per two elements instead of four; result within 2 fp16 ulps of the fp32 evaluation of k_gn_apply
+                    const float2 tt = __half22float2(h[k]);
+                    const __half2 hh = __floats2half2_rn(fmaf(tt.x, ca[2 * k], cb[2 * k]), fmaf(tt.y, ca[2 * k + 1], cb[2 * k + 1]));
+                    uint32_t hv = *reinterpret_cast<const uint32_t*>(&hh), tv;
+                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tv) : "r"(hv));
+                    const __half2 yy = __hfma2(hh, *reinterpret_cast<const __half2*>(&tv), hh);
+                    ow[k] = ok ? *reinterpret_cast<const uint32_t*>(&yy) : 0u;
                 }
+                if (n < 4 || p0 < 2u) sts128(dst + px * 128u + ((c8 ^ (px & 7u)) << 4), o);
             }
             fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&fullR[slot]);
             ++rctr;
+            advance(cu);
 #pragma unroll
             for (int n = 0; n < 5; ++n) { vcur[n] = vn1[n]; vn1[n] = vn2[n]; }
         }
