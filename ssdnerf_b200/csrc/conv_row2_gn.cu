@@ -30,9 +30,9 @@ constexpr int kGnRowBytes = 130 * 128;                   // one activation row: 
 constexpr int kGnRowSlot = 17 * 1024;                    // slot stride (1024-aligned)
 constexpr int kGnBSlot = kRwN * 128;                     // 16 KB weight tile
 constexpr int kGnMaxC = 384;
-template <int kGnRowSlots, int kGnBStages>
+template <bool PAIR>
 constexpr size_t gn_smem() {
-    return (size_t)kGnRowSlots * kGnRowSlot + (size_t)kGnBStages * kGnBSlot + 1024 /*align*/ + 256 /*barriers*/ + 512 /*qacc*/ +
+    return (size_t)(PAIR ? 8 : 6) * kGnRowSlot + (size_t)(PAIR ? 8 * (kGnBSlot / 2) : 6 * kGnBSlot) + 1024 /*align*/ + 512 /*barriers*/ + 512 /*qacc*/ +
            512 /*bias*/ + 8 * 2048 /*epilogue staging*/;
 }
 
@@ -46,41 +46,48 @@ struct ConvGnParams {
                                         // [4] loader wait free row, [5] loader total, [6] weight producer wait, [7] weight producer total
 };
 
-// kGnRowSlots activation rows + kGnBStages weight tiles share ~200 KB of shared memory (SSDNERF_GN_RING=66|75|84 selects the split)
-template <int kGnRowSlots, int kGnBStages>
+// PAIR: CTA pair with one tcgen05.mma.cta_group::2 (M = 256) per (tap, accumulator) for two consecutive tiles, as in conv_row2.cu: half the
+// MMA instructions and half the staged weight bytes per SM; the leader's MMA waits for the loader warps of BOTH CTAs (remote arrivals).
+// Single CTA: 6 rows + 6 weight tiles; pair: 8 rows + 8 half tiles (ring splits 6/6, 7/5, 8/4 measured identical).
+template <bool PAIR>
 __global__ void __launch_bounds__(kGnThreads, 1)
 k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int kGnRowSlots = PAIR ? 8 : 6, kGnBStages = PAIR ? 8 : 6, kBSlot = PAIR ? kGnBSlot / 2 : kGnBSlot;
     uint8_t* sR = smem;                                               // activation row ring
     uint8_t* sB = smem + kGnRowSlots * kGnRowSlot;
-    uint64_t* fullR = reinterpret_cast<uint64_t*>(sB + kGnBStages * kGnBSlot);
+    uint64_t* fullR = reinterpret_cast<uint64_t*>(sB + kGnBStages * kBSlot);
     uint64_t* emptyR = fullR + kGnRowSlots;
     uint64_t* fullB = emptyR + kGnRowSlots;
     uint64_t* emptyB = fullB + kGnBStages;
     uint64_t* tfull = emptyB + kGnBStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* qacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fullR) + 256);      // [32 quads][2]
+    float* qacc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fullR) + 512);      // [32 quads][2]  (36 mbarriers + TMEM slot < 512 B)
     float* sbias = qacc + 128;                                                             // [128]
     uint8_t* sstage = reinterpret_cast<uint8_t*>(sbias + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_per_img = p.H / 2, total_tiles = p.B * tiles_per_img;
     const uint32_t kc1 = p.C1 / 64, KC = (p.C1 + p.C2) / 64;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t tile0 = PAIR ? cluster_id_x() * 2u + crank : blockIdx.x;
+    const uint32_t tstep = PAIR ? num_clusters_x() * 2u : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapB);
-        for (int i = 0; i < kGnRowSlots; ++i) { mbar_init(&fullR[i], kGnLoaders / 32); mbar_init(&emptyR[i], 1); }     // every loader warp arrives once per row
+        for (int i = 0; i < kGnRowSlots; ++i) { mbar_init(&fullR[i], (kGnLoaders / 32) * (PAIR ? 2 : 1)); mbar_init(&emptyR[i], 1); }   // every loader warp (of both CTAs) arrives once per row
         for (int i = 0; i < kGnBStages; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128 * (PAIR ? 2 : 1)); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     for (int i = threadIdx.x; i < 64; i += kGnThreads) qacc[i] = 0.0f;
     for (int i = threadIdx.x; i < kRwN; i += kGnThreads) sbias[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
@@ -89,25 +96,32 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
     if (warp == 0) {   // ---------------- weight producer (TMA): for every (tile, chunk): 9 taps in (ky, kx) order
         uint32_t sb = 0, pb = 0;
         long long pw = 0; const long long q0 = clock64();
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t tile = tile0; tile < total_tiles; tile += tstep) {
             for (uint32_t j = 0; j < KC; ++j) {
                 for (uint32_t tap = 0; tap < 9; ++tap) {
                     if (p.prof) { const long long c_ = clock64(); mbar_wait(&emptyB[sb], pb ^ 1); pw += clock64() - c_; } else mbar_wait(&emptyB[sb], pb ^ 1);
-                    mbar_expect_tx_w(&fullB[sb], kGnBSlot);
-                    tma_load_4d_w(sB + sb * kGnBSlot, &mapB, &fullB[sb], (int)(j * 64), 0, (int)tap, 0);
+                    if (!PAIR) {
+                        mbar_expect_tx_w(&fullB[sb], kGnBSlot);
+                        tma_load_4d_w(sB + sb * kBSlot, &mapB, &fullB[sb], (int)(j * 64), 0, (int)tap, 0);
+                    } else {   // own half of the weight tile, bytes credited to the leader's barrier
+                        if (crank == 0) mbar_expect_tx_w(&fullB[sb], kGnBSlot);
+                        tma_load_4d_2cta_w(sB + sb * kBSlot, &mapB, mapa_u32(smem_u32(&fullB[sb]), 0), (int)(j * 64), (int)(crank * 64), (int)tap, 0);
+                    }
                     if (++sb == kGnBStages) { sb = 0; pb ^= 1; }
                 }
             }
         }
         if (p.prof && lane == 0) { atomicAdd(p.prof + 6, (unsigned long long)pw); atomicAdd(p.prof + 7, (unsigned long long)(clock64() - q0)); }
         __syncwarp();
-    } else if (warp == 1) {   // ---------------- MMA issuer (converged warp, elected lane)
-        constexpr uint32_t idesc = make_idesc_f16(128, kRwN);
+    } else if (warp == 1) {   // ---------------- MMA issuer (converged warp, elected lane; pair: the leader issues for both SMs)
+      if (!PAIR || crank == 0) {
+        constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, kRwN);
+        constexpr uint16_t kBoth = 3;
         uint32_t sb = 0, pb = 0, acc = 0, acc_phase = 0, rctr = 0;           // rctr: rows consumed so far (ring position of row 0 of the chunk)
         long long wr = 0, wb = 0, wt = 0; const long long m0 = clock64();
 #define GN_TIMED(acc_var, stmt) do { if (p.prof) { const long long c_ = clock64(); stmt; acc_var += clock64() - c_; } else { stmt; } } while (0)
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            GN_TIMED(wt, mbar_wait(&tempty[acc], acc_phase ^ 1));
+        for (uint32_t tile = tile0; tile < total_tiles; tile += tstep) {
+            if (PAIR) GN_TIMED(wt, mbar_wait_cluster(&tempty[acc], acc_phase ^ 1)); else GN_TIMED(wt, mbar_wait(&tempty[acc], acc_phase ^ 1));
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
             uint32_t started = 0;
@@ -117,50 +131,54 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
                 for (uint32_t r = 0; r < 4; ++r) { slot[r] = (rctr + r) % kGnRowSlots; rphase[r] = ((rctr + r) / kGnRowSlots) & 1u; }
 #pragma unroll
                 for (uint32_t ky = 0; ky < 3; ++ky) {
-                    if (ky == 0) { GN_TIMED(wr, mbar_wait(&fullR[slot[0]], rphase[0])); GN_TIMED(wr, mbar_wait(&fullR[slot[1]], rphase[1])); }
-                    else GN_TIMED(wr, mbar_wait(&fullR[slot[ky + 1]], rphase[ky + 1]));
+                    if (ky == 0) { GN_TIMED(wr, mbar_wait_cluster(&fullR[slot[0]], rphase[0])); GN_TIMED(wr, mbar_wait_cluster(&fullR[slot[1]], rphase[1])); }
+                    else GN_TIMED(wr, mbar_wait_cluster(&fullR[slot[ky + 1]], rphase[ky + 1]));
                     for (uint32_t kx = 0; kx < 3; ++kx) {
                         GN_TIMED(wb, mbar_wait(&fullB[sb], pb));
                         tc_fence_after();
-                        const uint64_t b_desc = make_desc_sw128(smem_u32(sB + sb * kGnBSlot));
+                        const uint64_t b_desc = make_desc_sw128(smem_u32(sB + sb * kBSlot));
 #pragma unroll
                         for (uint32_t a = 0; a < 2; ++a) {
                             const uint64_t a_desc = make_desc_sw128(smem_u32(sR + slot[ky + a] * kGnRowSlot) + kx * 128);
 #pragma unroll
-                            for (uint32_t k = 0; k < 4; ++k) umma_f16_w(d_tmem + a * kRwN, a_desc + 2 * k, b_desc + 2 * k, idesc, (started | k) != 0);
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                if (PAIR) umma_f16_2cta_w(d_tmem + a * kRwN, a_desc + 2 * k, b_desc + 2 * k, idesc, (started | k) != 0);
+                                else umma_f16_w(d_tmem + a * kRwN, a_desc + 2 * k, b_desc + 2 * k, idesc, (started | k) != 0);
+                            }
                         }
                         started = 1;
-                        umma_commit_w(&emptyB[sb]);
+                        if (PAIR) umma_commit_2cta_w(&emptyB[sb], kBoth); else umma_commit_w(&emptyB[sb]);
                         if (++sb == kGnBStages) { sb = 0; pb ^= 1; }
                     }
                     // rows whose last tap has been issued go back to the loaders
-                    umma_commit_w(&emptyR[slot[ky]]);
-                    if (ky == 2) umma_commit_w(&emptyR[slot[3]]);
+                    if (PAIR) umma_commit_2cta_w(&emptyR[slot[ky]], kBoth); else umma_commit_w(&emptyR[slot[ky]]);
+                    if (ky == 2) { if (PAIR) umma_commit_2cta_w(&emptyR[slot[3]], kBoth); else umma_commit_w(&emptyR[slot[3]]); }
                 }
                 rctr += 4;
             }
-            umma_commit_w(&tfull[acc]);
+            if (PAIR) umma_commit_2cta_w(&tfull[acc], kBoth); else umma_commit_w(&tfull[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (p.prof && lane == 0) {
             atomicAdd(p.prof + 0, (unsigned long long)wr); atomicAdd(p.prof + 1, (unsigned long long)wb); atomicAdd(p.prof + 2, (unsigned long long)wt);
             atomicAdd(p.prof + 3, (unsigned long long)(clock64() - m0));
         }
+      }
         __syncwarp();
     } else if (warp < 6) {   // ---------------- epilogue warps 2..5 (conv_row_epilogue.cuh): hidden behind the ~2x longer main loop of a tile
         const RowEpiArgs ea{p.H, p.residual, p.out, p.qstats};
-        conv_row_epilogue<4>(ea, warp, lane, total_tiles, tiles_per_img, tmem_base, tfull, tempty, sstage, sbias, qacc);
+        conv_row_epilogue<4, PAIR>(ea, warp, lane, total_tiles, tiles_per_img, tmem_base, tfull, tempty, sstage, sbias, qacc, tile0, tstep);
     } else {   // ---------------- activation loaders (warps 6..13): raw rows -> GroupNorm affine + SiLU -> swizzled operand rows
         const uint32_t lt = threadIdx.x - 192u;                       // 0..255
         const uint32_t c8 = lt & 7u, p0 = lt >> 3;                    // 16-byte chunk (8 channels) within the 64-channel row; pixels p0 + 32 n
         const uint32_t C = p.C1 + p.C2;
         // this CTA's rows form ONE stream over (tile, 64-channel chunk, row y0-1 .. y0+2); raw loads run two rows and the affine
         // coefficients one chunk ahead of the transform, across tile boundaries
-        const uint32_t my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint32_t my_tiles = tile0 < total_tiles ? (total_tiles - tile0 + tstep - 1) / tstep : 0;
         const uint32_t rpt = KC * 4u, n_rows = my_tiles * rpt;
         // stream position = (tile, row-within-tile w = 4 j + r), advanced without divisions
         struct Cur { uint32_t tile, w; };
-        auto advance = [&](Cur& c) { if (++c.w == rpt) { c.w = 0; c.tile += gridDim.x; } };
+        auto advance = [&](Cur& c) { if (++c.w == rpt) { c.w = 0; c.tile += tstep; } };
         auto issue_row = [&](const Cur& c, uint4* v) {                // raw 16-byte chunks of the row for pixels p0 + 32 n (zero outside the image)
             const uint32_t j = c.w >> 2, r = c.w & 3u;
             const uint32_t b = c.tile / tiles_per_img, y0 = (c.tile - b * tiles_per_img) * 2;
@@ -185,7 +203,7 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
         uint4 vcur[5], vn1[5], vn2[5];
         float4 cn[4];
         float ca[8], cb[8];
-        Cur cu{blockIdx.x, 0}, cl2{blockIdx.x, 0}, cc{blockIdx.x, 0};      // transform cursor, load cursor (2 rows ahead), coefficient cursor (next chunk)
+        Cur cu{tile0, 0}, cl2{tile0, 0}, cc{tile0, 0};      // transform cursor, load cursor (2 rows ahead), coefficient cursor (next chunk)
         if (n_rows) {
             issue_coef(cc, cn);
             issue_row(cl2, vcur); advance(cl2);
@@ -231,7 +249,7 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
             }
             fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(&fullR[slot]);
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&fullR[slot]), 0)); else mbar_arrive(&fullR[slot]); }
             ++rctr;
             advance(cu);
 #pragma unroll
@@ -241,7 +259,8 @@ k_conv_row2_gn(const __grid_constant__ CUtensorMap mapB, const ConvGnParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (PAIR) cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // per-(image, channel) GroupNorm affine, k_gn_apply arithmetic: y = x * a + b,
@@ -298,31 +317,43 @@ extern "C" int ssdnerf_conv3x3_gn_f16(const ssdnerf_conv_gn_args* a, void* strea
     ConvGnParams p{};
     p.B = a->B; p.H = a->H; p.x1 = (const __half*)a->x1; p.C1 = a->C1; p.x2 = (const __half*)a->x2; p.C2 = a->x2 ? a->C2 : 0;
     p.coef = (const float2*)a->coef_workspace; p.bias = a->bias; p.prof = (unsigned long long*)a->debug_cycles; p.residual = (const __half*)a->residual; p.out = (__half*)a->out; p.qstats = a->qstats;
-    CUtensorMap mB;
-    if (int e = make_map_4d_box(&mB, a->w, C, a->w_rows, 9, 1, (uint64_t)C * 2, (uint64_t)a->w_rows * C * 2, (uint64_t)9 * a->w_rows * C * 2, kRwN, 1, 1)) return e;
     int dev = 0, sms = 0;
     SSDNERF_CUDA_OK(cudaGetDevice(&dev));
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SSDNERF_CUDA_OK(launch_pdl(k_gn_coef, dim3(a->B), dim3(128), 0, stream, a->q1, a->C1, a->x2 ? a->q2 : (const float*)nullptr, p.C2, a->H * 128u,
                                a->gamma, a->beta, a->scale_shift, a->ss_batch_stride, a->eps, (float2*)a->coef_workspace));
     SSDNERF_LAUNCH_OK();
-    static int ring = 0;
-    if (!ring) { const char* e = getenv("SSDNERF_GN_RING"); ring = e ? atoi(e) : 66; }
     const uint32_t total = p.B * (p.H / 2);
-    const dim3 grid(total < (uint32_t)sms ? total : (uint32_t)sms);
-#define SSDNERF_GN_LAUNCH(R, S)                                                                                                           \
-    do {                                                                                                                                  \
-        static bool attr = false;                                                                                                         \
-        if (!attr) {                                                                                                                      \
-            SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2_gn<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn_smem<R, S>())); \
-            attr = true;                                                                                                                  \
-        }                                                                                                                                 \
-        SSDNERF_CUDA_OK(launch_pdl(k_conv_row2_gn<R, S>, grid, dim3(kGnThreads), gn_smem<R, S>(), stream, mB, p));                        \
-    } while (0)
-    if (ring == 84) SSDNERF_GN_LAUNCH(8, 4);
-    else if (ring == 75) SSDNERF_GN_LAUNCH(7, 5);
-    else SSDNERF_GN_LAUNCH(6, 6);
-#undef SSDNERF_GN_LAUNCH
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("SSDNERF_ROW2_PAIR"); pair_env = e ? atoi(e) : 1; }
+    const bool pair = pair_env && (p.H / 2) % 2 == 0 && total >= 2;
+    CUtensorMap mB;
+    if (int e = make_map_4d_box(&mB, a->w, C, a->w_rows, 9, 1, (uint64_t)C * 2, (uint64_t)a->w_rows * C * 2, (uint64_t)9 * a->w_rows * C * 2,
+                                pair ? kRwN / 2 : kRwN, 1, 1)) return e;
+    if (pair) {
+        static bool attr = false;
+        if (!attr) {
+            SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2_gn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn_smem<true>()));
+            attr = true;
+        }
+        const uint32_t clusters = (total / 2 < (uint32_t)sms / 2) ? total / 2 : (uint32_t)sms / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(kGnThreads); cfg.dynamicSmemBytes = gn_smem<true>(); cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        SSDNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_row2_gn<true>, mB, p));
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2_gn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn_smem<false>()));
+            attr = true;
+        }
+        SSDNERF_CUDA_OK(launch_pdl(k_conv_row2_gn<false>, dim3(total < (uint32_t)sms ? total : (uint32_t)sms), dim3(kGnThreads), gn_smem<false>(), stream, mB, p));
+    }
     SSDNERF_LAUNCH_OK();
     return 0;
 }

@@ -19,16 +19,18 @@ struct RowEpiArgs {
 };
 
 // NW = 8: warps 2..9, column half = (warp - 2) / 4;  NW = 4: warps 2..5, each warp walks both column halves
-template <int NW>
+// PAIR: the kernel runs as a CTA pair (one tcgen05.mma.cta_group::2 per two CTAs): tiles are indexed by cluster, `tile0` / `tstep`
+// are this CTA's first tile and stride, and the accumulator-free signal goes to the LEADER CTA's barrier
+template <int NW, bool PAIR = false>
 __device__ __forceinline__ void conv_row_epilogue(const RowEpiArgs& p, int warp, int lane, uint32_t total_tiles, uint32_t tiles_per_img,
                                                   uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, uint8_t* sstage,
-                                                  const float* sbias, float* qacc) {
+                                                  const float* sbias, float* qacc, uint32_t tile0 = blockIdx.x, uint32_t tstep = gridDim.x) {
     using namespace tc;
     const uint32_t q = (uint32_t)warp & 3u, hsel = (NW == 8) ? (uint32_t)(warp - 2) >> 2 : 0u;
     constexpr int kIts = (NW == 8) ? 4 : 8;               // (row a, column half, 32-column chunk) steps per warp and tile
     const uint32_t x = q * 32 + (uint32_t)lane;
     uint32_t acc = 0, acc_phase = 0;
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0; tile < total_tiles; tile += tstep) {
         const uint32_t b = tile / tiles_per_img, y0 = (tile - b * tiles_per_img) * 2;
         // global accesses re-mapped through a per-warp staging tile: one warp instruction = 8 pixels x 64 contiguous bytes (see gemm_tc.cu)
         const uint32_t wst = smem_u32(sstage) + (uint32_t)(warp - 2) * 2048u;     // shared-space address of this warp's staging tile
@@ -133,7 +135,7 @@ __device__ __forceinline__ void conv_row_epilogue(const RowEpiArgs& p, int warp,
             }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[acc]);
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]);
         if (p.qstats) {
             if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
             const uint32_t et = threadIdx.x - 64;
