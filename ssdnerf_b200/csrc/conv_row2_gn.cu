@@ -325,7 +325,7 @@ extern "C" int ssdnerf_conv3x3_gn_f16(const ssdnerf_conv_gn_args* a, void* strea
     SSDNERF_LAUNCH_OK();
     const uint32_t total = p.B * (p.H / 2);
     static int pair_env = -1;
-    if (pair_env < 0) { const char* e = getenv("SSDNERF_ROW2_PAIR"); pair_env = e ? atoi(e) : 1; }
+    if (pair_env < 0) { const char* e = getenv("SSDNERF_GN_PAIR"); pair_env = e ? atoi(e) : 0; }     // CTA-pair variant: opt-in until validated on hardware
     const bool pair = pair_env && (p.H / 2) % 2 == 0 && total >= 2;
     CUtensorMap mB;
     if (int e = make_map_4d_box(&mB, a->w, C, a->w_rows, 9, 1, (uint64_t)C * 2, (uint64_t)a->w_rows * C * 2, (uint64_t)9 * a->w_rows * C * 2,
