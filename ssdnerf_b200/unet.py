@@ -207,7 +207,9 @@ class UNetEngine:
     def __init__(self, m: DenoisingUnetMod, batch, device):
         self.m, self.B, self.dev = m, batch, torch.device(device)
         self.flash_attention = True      # False: unfused scores -> softmax -> PV composition (A/B tests)
-        self.fused_gn_conv = os.environ.get('SSDNERF_FUSED_GN_CONV', '1') != '0'   # 128x128-level resblocks: GN + SiLU inside the conv kernel
+        # 128x128-level resblocks: GroupNorm + SiLU inside the conv kernel (csrc/conv_row2_gn.cu).  Opt-in: measured 98 us per 128->128 layer
+        # against 22 + 59 us for the GroupNorm-apply pass + CTA-pair row-pair convolution (profiles/r01_gemm_pipeline_prof.txt)
+        self.fused_gn_conv = os.environ.get('SSDNERF_FUSED_GN_CONV', '0') == '1'
         self.H, self.W = m.image_size
         self.bufs = {}
         self.cin_total = m.in_channels + m.concat_cond_channels
