@@ -11,10 +11,10 @@ from tests.common import config1
 pytestmark = pytest.mark.gpu
 
 
-def _setup(cuda, variant='P'):
+def _setup(cuda, variant='P', res=64):
     from ssdnerf_b200 import renderer as R
     vid = R.DEC_P if variant == 'P' else R.DEC_S
-    code, poses, intr = config1(variant, seed=3)
+    code, poses, intr = config1(variant, seed=3, res=res)
     params = rp.make_decoder_params(variant, 3)
     blob = R.pack_decoder_blob(params, vid, device=cuda)
     planes = R.pack_planes(code.to(cuda), vid)
@@ -64,14 +64,15 @@ def test_empty_grid_and_empty_batches(cuda):
 
 def test_single_step_budget_and_train_ragged(cuda):
     """max_steps = 1 (one sample per ray, the coarsest legal march) and a 45-ray train-branch batch with gradient vs the oracle"""
-    R, vid, code, params, blob, planes, poses, intr = _setup(cuda)
+    R, vid, code, params, blob, planes, poses, intr = _setup(cuda, res=16)
     ro, rd = rp.get_cam_rays(poses[0], intr[0], 16, 16)
     ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
     bf = rp.sphere_bitfield()
     bft = torch.from_numpy(bf)[None].to(cuda)
     ref = rp.render_eval_scene(params, ro.numpy(), rd.numpy(), code[0], bf, max_steps=1, return_trace=True)
     out = R.render_fwd(vid, planes, (128, 128), bft, blob, rays_o=ro[None].to(cuda), rays_d=rd[None].to(cuda), max_steps=1)
-    assert np.array_equal(out['num_samples'][0].cpu().numpy(), np.array([len(t) for t in ref['trace']], np.int32))
+    cnt1 = np.array([len(t) for t in ref['trace']], np.int32)
+    assert cnt1.max() >= 1 and np.array_equal(out['num_samples'][0].cpu().numpy(), cnt1)
     np.testing.assert_allclose(out['image'][0].cpu().numpy(), ref['image'], rtol=2e-4, atol=2e-5)
     sel = torch.linspace(0, 255, 45).long()                        # 45 rays spread over the image (not a multiple of 32), most hit the sphere
     ro45, rd45 = ro[sel].contiguous(), rd[sel].contiguous()
