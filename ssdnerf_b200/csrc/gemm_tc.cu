@@ -9,7 +9,9 @@
 // * B (weights [taps][N][K] or a batched operand) is K-major too; both land in 128B-swizzled smem tiles.
 // * tcgen05.mma (M=128, N=BN, K=16, fp16 x fp16 -> fp32) accumulates in TMEM; accumulators are double
 //   buffered so the epilogue of tile i overlaps the main loop of tile i+1.
-// * warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue (TMEM -> regs -> global).
+// * warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner; converged warp, elected lane), warps 2..9 = epilogue
+//   (TMEM -> regs -> bias / residual / GroupNorm quad statistics -> staged 64-byte row pieces -> global).
+// * cluster modes (CL): CTA pair with tcgen05.mma.cta_group::2 (auto for N = 256 tiles), multicast clusters of 4 / 8 (kept for A/B).
 //
 // Replaces on the reference path: cuDNN Conv2d 3x3/1x1, Conv1d qkv/proj and the attention einsums of
 // lib/models/architecture/ddpm/{denoising,modules}.py (+ mmgen 0.7.2 blocks), see ssdnerf_b200/unet.py.
