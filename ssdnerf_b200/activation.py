@@ -1,28 +1,39 @@
-"""Mirror of lib/ops/activation.py:8-44 (TruncExp): exp forward in fp32, gradient g * clamp(exp x, 1e-6, 1e6).
+"""Density activation of the module path: sigma = exp(x) with a bounded derivative.
 
-Inside the fused renderers the activation is folded into the decoder epilogue; this module serves callers
-that build a decoder out of nn.Modules."""
+API mirror of the reference's `lib/ops/activation.py` (`trunc_exp`, `TruncExp`, cited in SURVEY.md §8 a20): the forward value is the
+plain fp32 exponential, the backward multiplies the incoming gradient by the exponential limited to [1e-6, 1e6] so a saturated density
+neither kills nor explodes the gradient.  The fused renderers (csrc/render_*.cu, csrc/render_train.cu) fold the same rule into their
+decoder epilogue / backward; this module only serves callers that compose a decoder out of nn.Modules (per-op train branch).
+"""
 import torch
-import torch.nn as nn
-from torch.autograd import Function
+from torch import nn
+
+_GRAD_FLOOR, _GRAD_CEIL = 1e-6, 1e6
 
 
-class _trunc_exp(Function):
-    @staticmethod
-    def forward(ctx, x):
-        exp_x = torch.exp(x.float())
-        ctx.save_for_backward(exp_x)
-        return exp_x
+class _BoundedGradExp(torch.autograd.Function):
+    """y = exp(x) in float32;  dy/dx := min(max(y, 1e-6), 1e6)"""
 
     @staticmethod
-    def backward(ctx, g):
-        return g * ctx.saved_tensors[0].clamp(min=1e-6, max=1e6)
+    def forward(x):
+        return x.to(torch.float32).exp()
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(output)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (y,) = ctx.saved_tensors
+        return grad_out * torch.clamp(y, _GRAD_FLOOR, _GRAD_CEIL)
 
 
-trunc_exp = _trunc_exp.apply
+def trunc_exp(x):
+    return _BoundedGradExp.apply(x)
 
 
 class TruncExp(nn.Module):
-    @staticmethod
-    def forward(x):
-        return _trunc_exp.apply(x)
+    """nn.Module wrapper (registered under 'trunc_exp' in TriPlaneDecoder.activation_dict)"""
+
+    def forward(self, x):
+        return trunc_exp(x)
