@@ -1,7 +1,7 @@
 """ad-hoc timing of the fused renderer (not the bench contract; see bench.py)"""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from oracle import render_port as rp
 from ssdnerf_b200 import renderer as R
 from tests.common import spiral_poses

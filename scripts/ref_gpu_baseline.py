@@ -5,7 +5,7 @@ autocast.  Measurement tool only (not imported by the product)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle', '_ref'))
-import numpy as np, torch
+import torch
 import torch.nn.functional as F
 from oracle import render_port as rp, unet_port as up
 from bench import orbit_poses

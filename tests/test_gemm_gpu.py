@@ -1,5 +1,4 @@
 """tcgen05 GEMM / implicit-GEMM conv (C-ABI ssdnerf_gemm_f16) vs PyTorch fp32 on the same fp16-rounded operands."""
-import numpy as np
 import pytest
 import torch
 

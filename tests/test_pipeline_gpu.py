@@ -1,6 +1,5 @@
 """End-to-end plugin path on a small model: DiffusionNeRF.val_step (DDIM -> occupancy grid -> fused render) vs the oracle chain.
 The UNet runs fp16 tensor-core GEMMs, so the comparison is statistical (image-level), not bit-level."""
-import numpy as np
 import pytest
 import torch
 

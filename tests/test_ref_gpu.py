@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import render_port as rp
-from tests.common import config1, spiral_poses
+from tests.common import spiral_poses
 
 pytestmark = pytest.mark.gpu
 _REF_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')

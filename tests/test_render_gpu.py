@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 import torch
 
-import oracle as orc
 from oracle import render_port as rp
 from tests.common import config1, spiral_poses
 

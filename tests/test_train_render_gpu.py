@@ -12,7 +12,7 @@ import torch
 from oracle import render_port as rp
 from oracle import train_port as tp
 from oracle import unet_port as up
-from tests.common import config1, spiral_poses
+from tests.common import spiral_poses
 
 pytestmark = pytest.mark.gpu
 

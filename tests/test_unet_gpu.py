@@ -69,7 +69,6 @@ def test_glue_kernels(cuda):
 
 
 def test_attention_block_matches_oracle(cuda):
-    from ssdnerf_b200.unet import UNetEngine
     spec = up.unet_spec(**{k: v for k, v in SMALL.items() if k != 'use_scale_shift_norm'})
     sd = up.random_state_dict(spec, seed=3, std=0.05)
     m = _build(SMALL, sd, cuda)
