@@ -72,3 +72,47 @@ def test_unsupported_paths_fail_loudly():
     with pytest.raises(S._lib.SSDNeRFNativeError):
         m.render(m.decoder, torch.zeros(1, 3, 6, 128, 128), torch.zeros(1, 32768, dtype=torch.uint8), 8, 8,
                  torch.zeros(1, 1, 4), torch.zeros(1, 1, 4, 4))
+
+
+def test_guidance_host_logic():
+    """ray batches, loss modules, activations: the host-side pieces of the guided path (base_nerf.py:231-296) on CPU tensors"""
+    from ssdnerf_b200.nerf import DiffusionNeRF, MSELoss, RegLoss, TanhCode
+    from ssdnerf_b200.activation import trunc_exp
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(2, 3, 8, 8, 3, generator=g)                    # 2 scenes x 3 views x 8x8
+    ro, rd = torch.rand(2, 3, 8, 8, 3, generator=g), torch.rand(2, 3, 8, 8, 3, generator=g)
+    inds, nb = DiffusionNeRF.get_raybatch_inds(imgs, 50)
+    assert nb == 4 and [i.shape for i in inds] == [(2, 50), (2, 50), (2, 50), (2, 42)]
+    allidx = torch.cat(list(inds), dim=1)
+    assert all(torch.equal(torch.sort(allidx[s]).values, torch.arange(192)) for s in range(2))      # a permutation per scene
+    o, d, t = DiffusionNeRF.ray_sample(ro, rd, imgs, 50, sample_inds=inds[1])
+    assert o.shape == (2, 50, 3) and torch.equal(t[1], imgs.reshape(2, -1, 3)[1][inds[1][1]]) and torch.equal(d[0], rd.reshape(2, -1, 3)[0][inds[1][0]])
+    assert DiffusionNeRF.get_raybatch_inds(imgs, 192) == (None, None)                                # whole image fits: no sampling
+    o2, _, t2 = DiffusionNeRF.ray_sample(ro, rd, imgs, 4096)
+    assert o2.shape == (2, 192, 3) and torch.equal(t2, imgs.reshape(2, -1, 3))
+    a, b = torch.rand(5, 3, generator=g), torch.rand(5, 3, generator=g)
+    torch.testing.assert_close(MSELoss(loss_weight=20.0)(a, b), ((a - b) ** 2).mean() * 20.0)
+    torch.testing.assert_close(RegLoss(power=2, loss_weight=3e-3)(a), (a ** 2).mean() * 3e-3)
+    torch.testing.assert_close(RegLoss(power=1)(a - 0.5), (a - 0.5).abs().mean())
+    tc = TanhCode(scale=2)
+    x = torch.linspace(-3, 3, 13)
+    torch.testing.assert_close(tc.inverse(tc(x)), x, rtol=1e-4, atol=1e-4)
+    z = torch.tensor([-30.0, 0.5, 30.0], requires_grad=True)
+    trunc_exp(z).sum().backward()
+    torch.testing.assert_close(z.grad, torch.tensor([1e-6, float(np.exp(0.5)), 1e6]))
+
+
+def test_guided_sampling_contract():
+    """grad_through_unet=True (the reference default) needs the UNet backward and must say so; CPU tensors never reach a fallback"""
+    cfg = S.Config.fromfile(os.path.join(ROOT, 'configs', 'cars_uncond_b200.py'))
+    m = S.build_model(cfg.model, test_cfg=dict(cfg.test_cfg))
+    d = m.diffusion
+    with pytest.raises(NotImplementedError, match='grad_through_unet'):
+        d.pred_x_0(torch.zeros(1, 18, 128, 128), torch.tensor([10]), grad_guide_fn=lambda x: x.sum(), cfg=dict(clip_range=[-2, 2]))
+    with pytest.raises(S._lib.SSDNeRFNativeError):
+        m.val_guide(dict(cond_imgs=torch.zeros(1, 1, 8, 8, 3), cond_intrinsics=torch.ones(1, 1, 4), cond_poses=torch.eye(4).expand(1, 1, 4, 4)))
+    with pytest.raises(NotImplementedError):
+        m.val_optim({})
+    # the step-wise sampler is selected for guidance / langevin / eta > 0 and refuses image-conditioned denoisers
+    with pytest.raises(NotImplementedError, match='concat_cond'):
+        d._ddim_sample_stepwise(torch.zeros(1, 18, 128, 128), concat_cond=torch.zeros(1, 1, 3, 128, 128))
