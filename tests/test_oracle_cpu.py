@@ -197,3 +197,23 @@ def test_train_render_gradient_finite_differences():
         lm, _ = tp.render_loss(params, code - d, ro[None], rd[None], target, [bf], **kw)
         fd = float(lp - lm) / (2 * eps)
         assert abs(fd - float(flat[i])) <= 1e-5 * max(1.0, abs(fd)) + 2e-3 * abs(fd), (i, fd, float(flat[i]))
+
+
+def test_golden_train_branch():
+    """regression pin of the train / guidance-branch oracle: tests/golden/oracle_train_v1.npz (made by make_golden_train.py)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden_train', os.path.join(GOLDEN, 'make_golden_train.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    T = np.load(os.path.join(GOLDEN, 'oracle_train_v1.npz'))
+    out = mod.compute()
+    assert np.array_equal(out['march_rays'], T['march_rays'])                                    # integer (ray, offset, count) triples: exact
+    assert np.array_equal(out['march_deltas_head'].view(np.uint32), T['march_deltas_head'].view(np.uint32))
+    for k in ('ws', 'depth', 'image', 'out_rgb'):
+        np.testing.assert_allclose(out[k], T[k], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out['loss'], T['loss'], rtol=1e-10)
+    assert np.array_equal(out['grad_top_idx'][:8], T['grad_top_idx'][:8])
+    np.testing.assert_allclose(out['grad_top_val'], T['grad_top_val'], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(out['grad_abs_sum_per_plane'], T['grad_abs_sum_per_plane'], rtol=1e-8)
+    # domain properties: early-terminated rays exist at this threshold, weights are a sub-probability, blended colour stays in range
+    assert (T['ws'] > 0).sum() >= 5 and T['ws'].max() <= 1 + 1e-9 and T['out_rgb'].min() >= -0.01 and T['out_rgb'].max() <= 1.01
