@@ -313,7 +313,7 @@ def run_ours(args):
     }
     if side_S is not None:
         line['render_variant_S'] = side_S
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:          # reported baseline: rank 0 at N = 1 only
         line['cpu_baseline'] = cpu_reference_sample(quick=True)
     print(json.dumps(line))
     if world > 1:
