@@ -1,6 +1,6 @@
 """small render workload for ncu captures: python scripts/prof_render.py <P|P_TC|S> """
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import render_port as rp
 from ssdnerf_b200 import renderer as R

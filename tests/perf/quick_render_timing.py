@@ -1,6 +1,6 @@
 """ad-hoc timing of the fused renderer (not the bench contract; see bench.py)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import render_port as rp
 from ssdnerf_b200 import renderer as R

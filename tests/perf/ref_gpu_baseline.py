@@ -3,7 +3,7 @@ except -std=c++17) driven by the reference's host loop (base_volume_renderer.py:
 plain PyTorch/cuDNN modules in the reference's default precision (fp32 storage, TF32 convs allowed, cudnn.benchmark) plus fp16
 autocast.  Measurement tool only (not imported by the product)."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle', '_ref'))
 import torch
 import torch.nn.functional as F

@@ -2,7 +2,7 @@
 fused = ssdnerf_render_train_fwd + mse_render_loss + render_train_bwd;  per-op = march_rays_train -> torch point_decode -> composite
 (the reference's composition, on this library's kernels)."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import ssdnerf_b200 as S
 from ssdnerf_b200 import renderer as R
