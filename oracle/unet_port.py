@@ -1,12 +1,20 @@
-"""PyTorch-CPU fp32 restatement of the reference's denoising UNet and DDIM sampler -- TEST INFRASTRUCTURE ONLY.
+"""PyTorch fp32 restatement of the reference's denoising UNet and DDIM sampler -- TEST INFRASTRUCTURE ONLY.
 
 Constructor logic: lib/models/architecture/ddpm/denoising.py:106-187, modules.py:12-129 (reference).
-Forward semantics of the inherited blocks are restated from mmgen 0.7.2 (NOT under /root/reference, not
-installed; SURVEY.md Appendix B, tagged [mmgen-memory]) -- parity of these parts is UNPINNED until checked
-against the real package or a released checkpoint:
-    mmgen/models/architectures/ddpm/modules.py: TimeEmbedding, DenoisingResBlock.forward, NormWithEmbedding,
-    MultiHeadAttention.QKVAttention, DenoisingDownsample/Upsample.forward
-DDIM algebra: lib/models/diffusions/gaussian_diffusion.py:64-154 (schedules), :180-240 (pred_x_0), :264-331.
+DDIM algebra: lib/models/diffusions/gaussian_diffusion.py:64-154 (schedules), :180-240 (pred_x_0), :242-331.
+
+PINNING (tests/test_reference_pin_cpu.py against tests/golden/reference_v1.npz, which tests/golden/make_golden_ref.py
+produced by EXECUTING the reference's own denoising.py / modules.py / gaussian_diffusion.py / sampler.py with mmcv / mmgen
+stubbed): state-dict keys + shapes of the full-size model, the forward wiring (skip stack, concat order, attention head
+layout, time embedding path), d out / d x_t, every schedule table (bit-exact float64), pred_x_0 / p_sample_ddim /
+p_sample_langevin / ddim_sample incl. guidance through the UNet and w.r.t. x_0, and the SNR loss weights.
+STILL [mmgen-memory] (mmgen 0.7.2 is not under /root/reference and not installed): the bodies of
+TimeEmbedding, DenoisingResBlock.forward, NormWithEmbedding, MultiHeadAttention.QKVAttention and
+DenoisingDownsample/Upsample.forward -- the stubs that stood in for them when the fixtures were generated are the same
+restatement, so for these bodies the fixtures pin self-consistency only.
+
+Every function is device-agnostic torch: the GPU parity tests may run it on the CUDA device with TF32 disabled
+(`fp32_reference_mode()`) where the CPU would take minutes (full-size 50-step chains).
 """
 import math
 
@@ -123,7 +131,7 @@ def random_state_dict(spec, seed=0, std=0.02, nonzero_last=True):
 def time_embedding(sd, t, base):
     """[mmgen-memory] TimeEmbedding: sinusoidal (cos | sin) -> Linear -> SiLU -> Linear."""
     half = base // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     e = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     e = F.linear(e, sd['time_embedding.blocks.0.weight'], sd['time_embedding.blocks.0.bias'])
@@ -234,3 +242,91 @@ def ddim_sample(denoise_fn, noise, dv, num_timesteps=50, T=1000, clip_range=(-2,
         eps = (x_t - dv['sqrt_alphas_bar'][t] * x0) / dv['sqrt_one_minus_alphas_bar'][t]
         x_t = np.sqrt(ab_prev) * x0 + np.sqrt(1 - ab_prev - tilde_beta * eta ** 2) * eps
     return x_t
+
+
+def fp32_reference_mode():
+    """strict fp32 for the oracle when it runs on a CUDA device (the reference default would allow TF32 convs)"""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+
+
+def state_dict_to(sd, device):
+    return {k: v.to(device) for k, v in sd.items()}
+
+
+def pred_x_0(denoise_fn, x_t, t, dv, grad_guide_fn=None, clip_denoised=True, clip_range=(-1, 1), guidance_gain=1.0,
+             grad_through_unet=True, snr_weight_power=0.5, update_denoising_output=False):
+    """gaussian_diffusion.py:180-240, V parameterisation. t: int; denoise_fn(x, t[B]) -> v."""
+    B = x_t.size(0)
+    tt = torch.full((B,), int(t), dtype=torch.long, device=x_t.device)
+    sa = float(np.float32(dv['sqrt_alphas_bar'][int(t)]))        # the reference builds the table in x_t's dtype (:190-191)
+    s1 = float(np.float32(dv['sqrt_one_minus_alphas_bar'][int(t)]))
+    if grad_guide_fn is None:
+        with torch.no_grad():
+            v = denoise_fn(x_t, tt)
+            x0 = sa * x_t - s1 * v
+            if clip_denoised:
+                x0 = x0.clamp(*clip_range)
+        return x0, v
+    with torch.enable_grad():
+        if grad_through_unet:
+            x_in = x_t.detach().requires_grad_(True)
+            v = denoise_fn(x_in, tt)
+            x0 = sa * x_in - s1 * v
+            if clip_denoised:
+                x0 = x0.clamp(*clip_range)
+            grad = torch.autograd.grad(grad_guide_fn(x0), x_in)[0]
+        else:
+            with torch.no_grad():
+                v = denoise_fn(x_t, tt)
+                x0 = sa * x_t - s1 * v
+                if clip_denoised:
+                    x0 = x0.clamp(*clip_range)
+            x0 = x0.detach().requires_grad_(True)
+            grad = torch.autograd.grad(grad_guide_fn(x0), x0)[0]
+    x0 = x0.detach() - grad * ((s1 ** (2 - snr_weight_power * 2)) * (sa ** (snr_weight_power * 2 - 1)) * guidance_gain)
+    if clip_denoised:
+        x0 = x0.clamp(*clip_range)
+    v = v.detach()
+    if update_denoising_output:
+        v = (sa * x_t - x0) / s1
+    return x0, v
+
+
+def ddim_sample_guided(denoise_fn, noise, dv, cfg, T=1000, grad_guide_fn=None, langevin_noises=None):
+    """gaussian_diffusion.py:295-331 with guidance and langevin correction steps (:242-262); `cfg` = test_cfg dict;
+    `langevin_noises` = iterator of the tensors the reference would draw with `_get_noise_batch`."""
+    x_t = noise
+    ts = [int(t) for t in ddim_timesteps(T, cfg.get('num_timesteps', T))]
+    kw = dict(clip_denoised=cfg.get('clip_denoised', True), clip_range=cfg.get('clip_range', [-1, 1]), guidance_gain=cfg.get('guidance_gain', 1.0),
+              grad_through_unet=cfg.get('grad_through_unet', True), snr_weight_power=cfg.get('snr_weight_power', 0.5))
+    eta = cfg.get('eta', 0)
+    lsteps, lrange, ldelta = cfg.get('langevin_steps', 0), cfg.get('langevin_t_range', [0, 1000]), cfg.get('langevin_delta', 0.1)
+    for step, t in enumerate(ts):
+        t_prev = ts[step + 1] if step + 1 < len(ts) else -1
+        ab_prev = dv['alphas_bar'][t_prev] if t_prev >= 0 else dv['alphas_bar_prev'][0]
+        x0, _ = pred_x_0(denoise_fn, x_t, t, dv, grad_guide_fn=grad_guide_fn, **kw)
+        eps = (x_t - dv['sqrt_alphas_bar'][t] * x0) / dv['sqrt_one_minus_alphas_bar'][t]
+        x_t = np.sqrt(ab_prev) * x0 + np.sqrt(1 - ab_prev - dv['tilde_betas_t'][t] * eta ** 2) * eps
+        if lsteps > 0 and lrange[0] < t_prev < lrange[1]:
+            for _ in range(lsteps):
+                sigma = dv['sqrt_one_minus_alphas_bar'][t_prev]
+                x0, _ = pred_x_0(denoise_fn, x_t, t_prev, dv, grad_guide_fn=grad_guide_fn, **kw)
+                eps = (x_t - dv['sqrt_alphas_bar'][t_prev] * x0) / sigma
+                x_t = x_t - 0.5 * ldelta * sigma * eps + math.sqrt(ldelta) * sigma * next(langevin_noises)
+    return x_t
+
+
+def snr_weighted_loss_weight(dv, power, mode='V', min=-1, max=-1, bias=0, prob_power=0.0):
+    """lib/models/diffusions/sampler.py:15-46 -> float32 weight[T]"""
+    mean, std = dv['sqrt_alphas_bar'], dv['sqrt_one_minus_alphas_bar']
+    weight_x = (mean / std) ** (2 * power) + bias
+    if min > 0:
+        weight_x = weight_x.clip(min=min)
+    if max > 0:
+        weight_x = weight_x.clip(max=max)
+    raw = dict(EPS=weight_x * (std / mean) ** 2, START_X=weight_x, V=weight_x * std ** 2)[mode]
+    prob = raw ** prob_power
+    prob = prob / prob.sum()
+    return torch.from_numpy(raw / (prob * len(mean))).to(torch.float)

@@ -8,6 +8,7 @@ host (float64, like the reference's NumPy tables), the per-step time-embedding p
 step, and ONE captured CUDA graph (UNet forward + fused V->x0->eps->x_prev update, device-side step counter) is
 replayed `num_timesteps` times.
 """
+import math
 import os
 from copy import deepcopy
 
@@ -87,46 +88,67 @@ class GaussianDiffusion(nn.Module):
         self.tilde_mu_t_coef2 = np.sqrt(self.alphas) * (1 - self.alphas_bar_prev) / (1 - self.alphas_bar)
 
     # ------------------------------------------------------------------ single-step API
+    def _coef(self, x_t, table, t):
+        """the reference indexes a table rebuilt in x_t's dtype with the device timestep (gaussian_diffusion.py:190-191)"""
+        return x_t.new_tensor(table)[t].reshape(-1, 1, 1, 1)
+
+    def q_sample(self, x_0, t, noise=None):
+        """gaussian_diffusion.py:166-178"""
+        if noise is None:
+            noise = torch.randn_like(x_0)
+        idx = t.cpu()
+        mean = torch.from_numpy(self.sqrt_alphas_bar)[idx].float().to(x_0.device).reshape(-1, 1, 1, 1)
+        std = torch.from_numpy(self.sqrt_one_minus_alphas_bar)[idx].float().to(x_0.device).reshape(-1, 1, 1, 1)
+        return x_0 * mean + noise * std, mean, std
+
+    def _x0_from_output(self, x_t, out, sa, s1):
+        mode = self.denoising_mean_mode.upper()
+        if mode == 'EPS':
+            return (x_t - s1 * out) / sa
+        if mode == 'START_X':
+            return out
+        if mode == 'V':
+            return sa * x_t - s1 * out
+        raise AttributeError(f'Unknown denoising mean output type [{self.denoising_mean_mode}].')
+
     @torch.no_grad()
     def pred_x_0(self, x_t, t, grad_guide_fn=None, concat_cond=None, cfg=dict(), update_denoising_output=False):
-        """gaussian_diffusion.py:180-240.  Guidance differentiates `grad_guide_fn` w.r.t. x_0 (`grad_through_unet=False`
-        branch, :218-222); the reference's default of back-propagating through the denoiser needs a UNet backward
-         and raises."""
+        """gaussian_diffusion.py:180-240.  With `grad_guide_fn` the guidance gradient is taken w.r.t. x_t THROUGH the denoiser
+        (`grad_through_unet=True`, the reference default: the UNet's hand-written input-gradient pass, unet.py `_UNetInputGrad`)
+        or w.r.t. the clamped x_0 (`grad_through_unet=False`)."""
         clip_denoised = cfg.get('clip_denoised', True)
         clip_range = cfg.get('clip_range', [-1, 1])
         guidance_gain = cfg.get('guidance_gain', 1.0)
+        grad_through_unet = cfg.get('grad_through_unet', True)
         snr_weight_power = cfg.get('snr_weight_power', 0.5)
-        if grad_guide_fn is not None and cfg.get('grad_through_unet', True):
-            raise NotImplementedError('guidance with grad_through_unet=True needs the hand-written UNet backward (SURVEY.md §8 f1); '
-                                      'set test_cfg.grad_through_unet=False to differentiate w.r.t. x_0 on the fused renderer')
         num_batches = x_t.size(0)
         if not torch.is_tensor(t):
             t = torch.as_tensor(t, device=x_t.device)
         if t.dim() == 0 or len(t) != num_batches:
             t = t.expand(num_batches)
-        sa = x_t.new_tensor(self.sqrt_alphas_bar)[t].reshape(-1, 1, 1, 1)
-        s1 = x_t.new_tensor(self.sqrt_one_minus_alphas_bar)[t].reshape(-1, 1, 1, 1)
-        out = self.denoising(x_t, t, concat_cond=concat_cond)
-        mode = self.denoising_mean_mode.upper()
-        if mode == 'EPS':
-            x_0 = (x_t - s1 * out) / sa
-        elif mode == 'START_X':
-            x_0 = out
-        elif mode == 'V':
-            x_0 = sa * x_t - s1 * out
-        else:
-            raise AttributeError(f'Unknown denoising mean output type [{self.denoising_mean_mode}].')
-        if grad_guide_fn is not None:
-            if clip_denoised:
+        sa = self._coef(x_t, self.sqrt_alphas_bar, t)
+        s1 = self._coef(x_t, self.sqrt_one_minus_alphas_bar, t)
+        through = grad_guide_fn is not None and grad_through_unet
+        if through:
+            x_t = x_t.detach().requires_grad_(True)
+        with torch.set_grad_enabled(through):
+            out = self.denoising(x_t, t, concat_cond=concat_cond)
+            x_0 = self._x0_from_output(x_t, out, sa, s1)
+            if grad_guide_fn is not None and clip_denoised:
                 x_0 = x_0.clamp(*clip_range)
-            with torch.enable_grad():
-                x_0 = x_0.detach().requires_grad_(True)
-                loss = grad_guide_fn(x_0)
-                grad = torch.autograd.grad(loss, x_0)[0]
+            if through:
+                grad = torch.autograd.grad(grad_guide_fn(x_0), x_t)[0]
+        if grad_guide_fn is not None:
+            if not through:
+                with torch.enable_grad():
+                    x_0 = x_0.detach().requires_grad_(True)
+                    grad = torch.autograd.grad(grad_guide_fn(x_0), x_0)[0]
+            x_t, out = x_t.detach(), out.detach()
             x_0 = x_0.detach() - grad * ((s1 ** (2 - snr_weight_power * 2)) * (sa ** (snr_weight_power * 2 - 1)) * guidance_gain)
         if clip_denoised:
             x_0 = x_0.clamp(*clip_range)
         if update_denoising_output and grad_guide_fn is not None:
+            mode = self.denoising_mean_mode.upper()
             if mode == 'EPS':
                 out = (x_t - x_0 * sa) / s1
             elif mode == 'START_X':
@@ -145,7 +167,7 @@ class GaussianDiffusion(nn.Module):
         eps_t_pred = (x_t - float(self.sqrt_alphas_bar[t]) * x_0_pred) / sigma
         if noise is None:
             noise = torch.randn_like(x_t)
-        return x_t - 0.5 * langevin_delta * sigma * eps_t_pred + float(np.sqrt(langevin_delta)) * sigma * noise
+        return x_t - 0.5 * langevin_delta * sigma * eps_t_pred + math.sqrt(langevin_delta) * sigma * noise
 
     @torch.no_grad()
     def p_sample_ddim(self, x_t, t, t_prev, noise=None, cfg=dict(), grad_guide_fn=None, **kwargs):
@@ -164,9 +186,11 @@ class GaussianDiffusion(nn.Module):
         return x_prev, x_0_pred
 
     @torch.no_grad()
-    def _ddim_sample_stepwise(self, noise, concat_cond=None, save_intermediates=False, grad_guide_fn=None, **kwargs):
+    def _ddim_sample_stepwise(self, noise, concat_cond=None, save_intermediates=False, grad_guide_fn=None, langevin_noises=None,
+                              show_pbar=False, **kwargs):
         """gaussian_diffusion.py:295-331 step by step (host timesteps: no device->host sync): guidance, langevin
-        correction steps, eta > 0 and `save_intermediates`.  The unguided eta=0 loop uses the captured graph instead."""
+        correction steps, eta > 0 and `save_intermediates`.  The unguided eta=0 loop uses the captured graph instead.
+        `langevin_noises`: optional iterator of the tensors the langevin steps add (parity tests; default torch.randn)."""
         if concat_cond is not None:
             raise NotImplementedError('concat_cond (image-conditioned denoiser) is not used by the shipped configs')
         cfg = self.test_cfg
@@ -181,7 +205,8 @@ class GaussianDiffusion(nn.Module):
             x_t, x_0_pred = self.p_sample_ddim(x_t, t, t_prev, cfg=cfg, grad_guide_fn=grad_guide_fn, **kwargs)
             if langevin_steps > 0 and langevin_t_range[0] < t_prev < langevin_t_range[1]:
                 for _ in range(langevin_steps):
-                    x_t = self.p_sample_langevin(x_t, t_prev, cfg=cfg, grad_guide_fn=grad_guide_fn, **kwargs)
+                    x_t = self.p_sample_langevin(x_t, t_prev, cfg=cfg, grad_guide_fn=grad_guide_fn,
+                                                 noise=next(langevin_noises) if langevin_noises is not None else None, **kwargs)
             if out is not None:
                 out.extend([x_0_pred, x_t])
         return out if save_intermediates else x_t

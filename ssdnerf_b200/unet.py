@@ -161,8 +161,8 @@ class DenoisingUnetMod(nn.Module):
                     scale //= 2
                 self.out_blocks.append(nn.Sequential(*layers))
         self.out = nn.Module()
+        self.out.conv = nn.Conv2d(cin, in_channels, 3, padding=1)       # mmcv ConvModule registers conv before the norm
         self.out.gn = _gn(cin)
-        self.out.conv = nn.Conv2d(cin, in_channels, 3, padding=1)
         self._engine = None
         self._engine_key = None
 

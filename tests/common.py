@@ -48,3 +48,25 @@ def config1(variant='S', seed=0, res=64):
 def rel_err(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def seeded_weights(keys, shapes, seed):
+    """State-dict tensors drawn from one seeded CPU generator in key order (GroupNorm gains ~1, other vectors ~0.1 N(0,1),
+    matrices / kernels N(0, 1.5/sqrt(fan_in))).  tests/golden/make_golden_ref.py loads exactly these into the reference's
+    own modules, so the committed fixtures need only the key / shape lists and the seed."""
+    import math
+    g = torch.Generator().manual_seed(int(seed))
+    sd = {}
+    for k, shape in zip(keys, shapes):
+        shape = tuple(int(s) for s in shape)
+        if len(shape) == 1 and (k.endswith('norm.weight') or k.endswith('.0.weight') or k.endswith('gn.weight')):
+            sd[k] = 1 + 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[k] = 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[k] = torch.randn(shape, generator=g) * (1.5 / math.sqrt(int(np.prod(shape[1:]))))
+    return sd
+
+
+def parse_shapes(arr):
+    return [tuple(int(x) for x in s.split(',')) if s else () for s in arr.tolist()]

@@ -1,0 +1,154 @@
+"""Pins the oracle (oracle/unet_port.py) and the package's host-side diffusion logic to fixtures produced by EXECUTING the
+reference's own denoising.py / modules.py / gaussian_diffusion.py / sampler.py (tests/golden/make_golden_ref.py, run in the build
+container; which lines ran from /root/reference and which were mmgen stubs is listed in that file's header).
+
+Bars: float64 schedule tables bit-exact; fp32 tensors to 2e-5 absolute on O(1) values (same arithmetic, different op order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_port as up
+from tests.common import GOLDEN, parse_shapes, seeded_weights
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return np.load(os.path.join(GOLDEN, 'reference_v1.npz'))
+
+
+SMALL = dict(image_size=16, in_channels=18, base_channels=32, channels_cfg=(1, 2, 2), resblocks_per_downsample=2,
+             attention_res=(8, 4), num_heads=2)
+TEST_CFG = dict(num_timesteps=10, clip_range=[-2, 2], guidance_gain=37.5, snr_weight_power=0.25, langevin_steps=2, langevin_delta=0.4)
+
+
+def _small(ref):
+    keys, shapes = ref['unet_keys'].tolist(), parse_shapes(ref['unet_shapes'])
+    sd = seeded_weights(keys, shapes, int(ref['unet_weight_seed']))
+    assert abs(sum(float(v.double().sum()) for v in sd.values()) - float(ref['unet_weight_checksum'])) < 1e-6
+    return up.unet_spec(**SMALL), sd
+
+
+def _close(a, b, atol=2e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() <= atol, float(np.abs(a - b).max())
+
+
+def test_state_dict_layout_matches_reference_constructor(ref):
+    """keys + shapes the REFERENCE constructor produces (denoising.py:106-187) == the oracle's enumeration == the package's module"""
+    spec = up.unet_spec()
+    sd = up.random_state_dict(spec, seed=0)
+    ref_keys, ref_shapes = ref['full_keys'].tolist(), parse_shapes(ref['full_shapes'])
+    assert sorted(sd.keys()) == sorted(ref_keys)
+    for k, s in zip(ref_keys, ref_shapes):
+        assert tuple(sd[k].shape) == s, k
+    assert int(ref['full_numel']) == sum(v.numel() for v in sd.values()) == 122434194
+    from ssdnerf_b200.unet import DenoisingUnetMod
+    m = DenoisingUnetMod(image_size=128, in_channels=18, base_channels=128, channels_cfg=[1, 2, 2, 4, 4], resblocks_per_downsample=2,
+                         use_scale_shift_norm=True, num_heads=4, attention_res=[32, 16, 8])
+    msd = m.state_dict()
+    assert list(msd.keys()) == ref_keys                      # same ORDER too (checkpoint loaders may rely on it)
+    assert [tuple(v.shape) for v in msd.values()] == ref_shapes
+    md = DenoisingUnetMod(image_size=128, in_channels=18, base_channels=128, channels_cfg=[1, 2, 2, 4, 4], resblocks_per_downsample=2,
+                          dropout=0.1, use_scale_shift_norm=True, num_heads=4, attention_res=[32, 16, 8])
+    assert list(md.state_dict().keys()) == ref['full_dropout_keys'].tolist()     # conv_2.2 when dropout > 0
+
+
+def test_unet_forward_and_input_gradient(ref):
+    spec, sd = _small(ref)
+    assert sorted(sd.keys()) == sorted(up.random_state_dict(spec).keys())
+    x, t = torch.from_numpy(ref['unet_x']), torch.from_numpy(ref['unet_t'])
+    _close(up.unet_forward(sd, spec, x, t), ref['unet_y'])
+    xr = x.clone().requires_grad_(True)
+    (up.unet_forward(sd, spec, xr, t) * torch.from_numpy(ref['unet_r'])).sum().backward()
+    _close(xr.grad, ref['unet_dx'])
+
+
+def test_schedule_tables_bit_exact(ref):
+    dv = up.diffusion_vars(up.linear_betas())
+    for k in ('betas', 'alphas_bar', 'alphas_bar_prev', 'sqrt_alphas_bar', 'sqrt_one_minus_alphas_bar', 'tilde_betas_t'):
+        assert np.array_equal(dv[k], ref['lin_' + k]), k
+    from ssdnerf_b200.diffusion import GaussianDiffusion
+    d = GaussianDiffusion(denoising=torch.nn.Identity(), betas_cfg=dict(type='linear'), num_timesteps=1000)
+    for k in ('betas', 'alphas_bar', 'alphas_bar_prev', 'sqrt_alphas_bar', 'sqrt_one_minus_alphas_bar', 'sqrt_recip_alplas_bar',
+              'sqrt_recipm1_alphas_bar', 'tilde_betas_t', 'log_tilde_betas_t_clipped', 'tilde_mu_t_coef1', 'tilde_mu_t_coef2'):
+        assert np.array_equal(np.asarray(getattr(d, k), np.float64), ref['lin_' + k]), k
+    dc = GaussianDiffusion(denoising=torch.nn.Identity(), betas_cfg=dict(type='cosine'), num_timesteps=1000)
+    assert np.array_equal(dc.alphas_bar, ref['cos_alphas_bar'])
+    assert np.array_equal(up.snr_weighted_loss_weight(dv, 0.25, 'V').numpy(), ref['snr_weight_p025_V'])
+
+
+def _oracle_denoiser(ref):
+    spec, sd = _small(ref)
+    return lambda x, t: up.unet_forward(sd, spec, x, t)
+
+
+def test_oracle_sampler_algebra(ref):
+    den = _oracle_denoiser(ref)
+    dv = up.diffusion_vars(up.linear_betas())
+    x_t = torch.from_numpy(ref['x_t'])
+    x0, v = up.pred_x_0(den, x_t, 600, dv, clip_range=(-2, 2))
+    _close(x0, ref['pred_x0_t600']); _close(v, ref['pred_v_t600'])
+    _close(up.ddim_sample(den, x_t, dv, num_timesteps=10, clip_range=(-2, 2)), ref['ddim10'], 5e-5)
+    target = torch.from_numpy(ref['guide_target'])
+    guide = lambda x0: 0.5 * ((x0 - target) ** 2).mean() * x0.size(0)
+    for through, tag in ((True, 'thru'), (False, 'x0')):
+        x0, v = up.pred_x_0(den, x_t, 600, dv, grad_guide_fn=guide, clip_range=(-2, 2), guidance_gain=37.5, snr_weight_power=0.25,
+                            grad_through_unet=through, update_denoising_output=True)
+        _close(x0, ref[f'guided_x0_{tag}']); _close(v, ref[f'guided_v_{tag}'], 1e-4)
+    g2 = torch.Generator().manual_seed(int(ref['langevin_noise_seed']))
+    noises = iter([torch.randn(2, 18, 16, 16, generator=g2) for _ in range(18)])
+    out = up.ddim_sample_guided(den, x_t, dv, dict(TEST_CFG, langevin_t_range=[0, 1000]), grad_guide_fn=guide, langevin_noises=noises)
+    _close(out, ref['guided_langevin_ddim10'], 2e-4)
+
+
+class _OracleUNet(torch.nn.Module):
+    """oracle UNet behind the nn.Module interface `GaussianDiffusion` drives (CPU stand-in for the CUDA engine)"""
+
+    def __init__(self, ref):
+        super().__init__()
+        self.spec, sd = _small(ref)
+        self.sd = torch.nn.ParameterDict({k.replace('.', '/'): torch.nn.Parameter(v) for k, v in sd.items()})
+
+    def forward(self, x_t, t, label=None, concat_cond=None):
+        sd = {k.replace('/', '.'): v for k, v in self.sd.items()}
+        return up.unet_forward(sd, self.spec, x_t, t)
+
+
+def test_package_sampler_host_logic_matches_reference(ref):
+    """ssdnerf_b200.GaussianDiffusion's step-wise loop (pred_x_0 both guidance routes, p_sample_ddim incl. eta, langevin,
+    save_intermediates) on CPU with the oracle UNet as denoiser == what the reference's own loop produced."""
+    from ssdnerf_b200.diffusion import GaussianDiffusion
+    d = GaussianDiffusion(denoising=_OracleUNet(ref), betas_cfg=dict(type='linear'), num_timesteps=1000, test_cfg=dict(TEST_CFG))
+    x_t = torch.from_numpy(ref['x_t'])
+    x0, v = d.pred_x_0(x_t.clone(), torch.tensor(600), cfg=TEST_CFG)
+    _close(x0, ref['pred_x0_t600']); _close(v, ref['pred_v_t600'])
+    xp, _ = d.p_sample_ddim(x_t.clone(), 600, 500, cfg=TEST_CFG)
+    _close(xp, ref['ddim_prev_600_500'])
+    xp, _ = d.p_sample_ddim(x_t.clone(), 99, -1, cfg=TEST_CFG)
+    _close(xp, ref['ddim_prev_99_last'])
+    r = torch.from_numpy(ref['unet_r'])
+    xp, _ = d.p_sample_ddim(x_t.clone(), 600, 500, noise=r, cfg=dict(TEST_CFG, eta=0.7))
+    _close(xp, ref['ddim_prev_600_500_eta07'])
+    _close(d.p_sample_langevin(x_t.clone(), 500, noise=r, cfg=TEST_CFG), ref['langevin_500'])
+    d.test_cfg = dict(TEST_CFG, langevin_steps=0)
+    inter = d.ddim_sample(x_t.clone(), save_intermediates=True)
+    assert len(inter) == 20
+    _close(torch.stack([inter[i] for i in (0, 1, 2, 3, 18, 19)]), ref['ddim10_intermediates_0_1_2_3_18_19'], 5e-5)
+    _close(inter[-1], ref['ddim10'], 5e-5)
+    target = torch.from_numpy(ref['guide_target'])
+    guide = lambda x0: 0.5 * ((x0 - target) ** 2).mean() * x0.size(0)
+    for through, tag in ((True, 'thru'), (False, 'x0')):
+        cfg = dict(TEST_CFG, grad_through_unet=through)
+        x0, v = d.pred_x_0(x_t.clone(), torch.tensor(600), grad_guide_fn=guide, cfg=cfg, update_denoising_output=True)
+        _close(x0, ref[f'guided_x0_{tag}']); _close(v, ref[f'guided_v_{tag}'], 1e-4)
+    g2 = torch.Generator().manual_seed(int(ref['langevin_noise_seed']))
+    noises = [torch.randn(2, 18, 16, 16, generator=g2) for _ in range(18)]
+    d.test_cfg = dict(TEST_CFG, langevin_t_range=[0, 1000])
+    out = d.ddim_sample(x_t.clone(), grad_guide_fn=guide, langevin_noises=iter(noises))
+    _close(out, ref['guided_langevin_ddim10'], 2e-4)
+    eps = torch.from_numpy(ref['q_eps'])
+    xq, mean, std = d.q_sample(target, torch.tensor([10, 900]), noise=eps)
+    _close(xq, ref['q_sample'])
