@@ -114,6 +114,13 @@ SSDNERF_API size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, ui
 SSDNERF_API int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, uint32_t Hp, uint32_t Wp, void* planes,
                         void* stream);
 
+/* Stand-alone point decode (variant P): sigma [M] (and rgb [M][3] when `rgbs` != NULL) at M points given as the concatenation
+ * of per-scene point lists; scene_offsets [B+1] (int64, device) holds the prefix sums, scene_offsets[B] == M.
+ *   replaces: lib/models/decoders/triplane_decoder.py:104-117 (xyz_transform), :119-179 (point_decode), :181-184 (point_density_decode) */
+SSDNERF_API int ssdnerf_point_decode(int variant, const void* planes, uint32_t plane_h, uint32_t plane_w, const float* decoder_blob,
+                                     const float* xyzs, const float* dirs, const long long* scene_offsets, uint32_t num_scenes,
+                                     unsigned long long num_points, float* sigmas, float* rgbs, void* stream);
+
 typedef struct ssdnerf_render_args {
     int variant;              /* SSDNERF_DEC_* */
     uint32_t num_scenes;      /* B */

@@ -160,10 +160,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_flash_attn(const __half* __restr
 template <int CH, int WARPS>
 static int launch_flash(const __half* qkv, uint32_t B, uint32_t T, uint32_t heads, float scale, __half* out, cudaStream_t stream) {
     constexpr size_t smem = (size_t)(WARPS * 16 + 4 * kFaBN) * (CH * 2 + 16);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_flash_attn<CH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     SSDNERF_CUDA_OK(launch_pdl(k_flash_attn<CH, WARPS>, dim3(T / (WARPS * 16), B * heads), dim3(WARPS * 32), smem, stream, qkv, T, heads,
                                scale * 1.4426950408889634f, out));

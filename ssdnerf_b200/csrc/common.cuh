@@ -33,6 +33,14 @@ int set_error_msg(int code, const char* msg);
 
 __host__ __device__ inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+// Function attributes (dynamic shared-memory opt-in) and occupancy numbers are PER DEVICE: launch sites key their one-time set-up by
+// the current device ordinal so a process that drives several GPUs configures each of them.
+inline int current_device() { int d = 0; (void)cudaGetDevice(&d); return d & 63; }
+struct DeviceOnce {
+    bool done[64] = {};
+    bool first() { const int d = current_device(); if (done[d]) return false; done[d] = true; return true; }
+};
+
 // Programmatic dependent launch (PDL): consecutive kernels of the DDIM step are launched with the programmatic-stream-serialization
 // attribute, so the next kernel's CTAs may start (barrier init, TMEM allocation, weight / bias staging) while the tail of the current
 // one drains.  pdl_wait() blocks until the preceding kernel has completed and its writes are visible: nothing produced by an earlier

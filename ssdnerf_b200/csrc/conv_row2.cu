@@ -202,10 +202,9 @@ int conv_row2_launch(const ssdnerf_gemm_args* a, int sms, cudaStream_t stream) {
     if (int e = make_map_4d_box(&mB, a->b, ktot, a->n_rows_b ? a->n_rows_b : a->n, a->bx2 ? a->bx2 : 1, a->bx3 ? a->bx3 : 1, a->b_strides[0],
                                 a->b_strides[1], a->b_strides[2], pair ? kRwN / 2 : kRwN, 1, 1)) return e;
     if (pair) {
-        static bool attr = false;
-        if (!attr) {
+        static DeviceOnce attr;
+        if (attr.first()) {
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRwSmemPair));
-            attr = true;
         }
         const uint32_t clusters = (total / 2 < (uint32_t)sms / 2) ? total / 2 : (uint32_t)sms / 2;
         cudaLaunchConfig_t cfg{};
@@ -218,10 +217,9 @@ int conv_row2_launch(const ssdnerf_gemm_args* a, int sms, cudaStream_t stream) {
         cfg.attrs = at; cfg.numAttrs = 2;
         SSDNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_row2<true>, mA1, mA2, mB, p));
     } else {
-        static bool attr = false;
-        if (!attr) {
+        static DeviceOnce attr;
+        if (attr.first()) {
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRwSmem));
-            attr = true;
         }
         SSDNERF_CUDA_OK(launch_pdl(k_conv_row2<false>, dim3(total < (uint32_t)sms ? total : (uint32_t)sms), dim3(kRwThreads), kRwSmem, stream, mA1, mA2, mB, p));
     }

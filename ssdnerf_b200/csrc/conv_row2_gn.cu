@@ -331,10 +331,9 @@ extern "C" int ssdnerf_conv3x3_gn_f16(const ssdnerf_conv_gn_args* a, void* strea
     if (int e = make_map_4d_box(&mB, a->w, C, a->w_rows, 9, 1, (uint64_t)C * 2, (uint64_t)a->w_rows * C * 2, (uint64_t)9 * a->w_rows * C * 2,
                                 pair ? kRwN / 2 : kRwN, 1, 1)) return e;
     if (pair) {
-        static bool attr = false;
-        if (!attr) {
+        static DeviceOnce attr;
+        if (attr.first()) {
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2_gn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn_smem<true>()));
-            attr = true;
         }
         const uint32_t clusters = (total / 2 < (uint32_t)sms / 2) ? total / 2 : (uint32_t)sms / 2;
         cudaLaunchConfig_t cfg{};
@@ -347,10 +346,9 @@ extern "C" int ssdnerf_conv3x3_gn_f16(const ssdnerf_conv_gn_args* a, void* strea
         cfg.attrs = at; cfg.numAttrs = 2;
         SSDNERF_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_row2_gn<true>, mB, p));
     } else {
-        static bool attr = false;
-        if (!attr) {
+        static DeviceOnce attr;
+        if (attr.first()) {
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_conv_row2_gn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn_smem<false>()));
-            attr = true;
         }
         SSDNERF_CUDA_OK(launch_pdl(k_conv_row2_gn<false>, dim3(total < (uint32_t)sms ? total : (uint32_t)sms), dim3(kGnThreads), gn_smem<false>(), stream, mB, p));
     }

@@ -310,11 +310,10 @@ int ssdnerf_density_update(int variant, const void* planes, uint32_t plane_h, ui
     if (is_s) {
         const uint32_t blocks_s = (uint32_t)((total + kDenThreads - 1) / kDenThreads);
         const size_t smem = (96 * 128 + 256) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.first()) {
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_density_update_s<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_density_update_s<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
         }
         if (grid_is_half)
             k_density_update_s<__half><<<blocks_s, kDenThreads, smem, stream>>>((const __half*)planes, plane_h, plane_w, decoder_blob, num_scenes,

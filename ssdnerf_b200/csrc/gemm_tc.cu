@@ -446,10 +446,9 @@ template <int BN, int CL>
 static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mB, const GemmParams& p, int sms,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CL>;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-        attr = true;
     }
     const uint32_t tiles_m = p.T1 * p.T2 * p.T3;
     const uint32_t total = ((tiles_m + CL - 1) / CL) * p.tiles_n;          // work items per cluster (CL = 1: per CTA)
@@ -463,7 +462,8 @@ static int launch_gemm(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUt
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 2;
-    static int max_clusters_cached = 0;      // co-resident clusters of this instantiation (1 CTA / SM; GPC sizes limit clusters of 4 / 8)
+    static int max_clusters_dev[64] = {};     // co-resident clusters of this instantiation (1 CTA / SM; GPC sizes limit clusters of 4 / 8)
+    int& max_clusters_cached = max_clusters_dev[current_device()];
     if (!max_clusters_cached) {
         max_clusters_cached = sms / CL;
         if (CL > 2) {

@@ -359,10 +359,9 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
         if (!occ_choice) { const char* e = getenv("SSDNERF_P_OCC"); occ_choice = (e && e[0] == '4') ? 4 : 3; }
         const size_t smem = sizeof(SmemP);
         auto kern = occ_choice == 3 ? k_render_p<3> : k_render_p<4>;
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[occ_choice - 3]) {
+        static DeviceOnce attr_set[2];
+        if (attr_set[occ_choice - 3].first()) {
             SSDNERF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[occ_choice - 3] = true;
         }
         int occ = 0;
         SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem));

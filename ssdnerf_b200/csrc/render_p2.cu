@@ -292,10 +292,9 @@ __global__ void __launch_bounds__(kP2Threads, MINB) k_render_p2(RenderParams p, 
 int render_p2_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream) {
     const size_t smem = sizeof(SmemP2);
     auto kern = k_render_p2<3>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     int occ = 0;
     SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kP2Threads, smem));

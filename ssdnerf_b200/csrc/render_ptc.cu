@@ -320,10 +320,9 @@ __global__ void __launch_bounds__(kPThreads, 2) k_render_ptc(RenderParams p, int
 
 int render_ptc_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream) {
     const size_t smem = sizeof(SmemPT) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_render_ptc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     int occ = 0;
     SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_ptc, kPThreads, smem));

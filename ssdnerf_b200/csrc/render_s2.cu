@@ -328,10 +328,9 @@ __global__ void __launch_bounds__(kS2Threads, 2) k_render_s2(RenderParams p, int
 
 int render_s2_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream) {
     const size_t smem = sizeof(SmemS2);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(k_render_s2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     int occ = 0;
     SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_s2, kS2Threads, smem));

@@ -374,10 +374,9 @@ static int train_launch(const ssdnerf_render_train_args* a, bool bwd, cudaStream
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = sizeof(SmemT);
     auto kern = bwd ? k_render_train_p<true> : k_render_train_p<false>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[bwd]) {
+    static DeviceOnce attr_set[2];
+    if (attr_set[bwd].first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[bwd] = true;
     }
     int occ = 0;
     SSDNERF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCtaThreads, smem));

@@ -8,18 +8,15 @@ return_loss)` returning `dict(weights_sum, depth, image)` as per-scene lists in 
 
 eval mode (`self.training == False`): ONE fused launch sequence (csrc/render_fused.cu, csrc/render_tc.cu).
 train mode: frozen decoder of the shipped-config shape (guidance / code optimisation, diffusion_nerf.py:273) ->
-fused differentiable renderer (csrc/render_train.cu, gradient w.r.t. the code only); otherwise the reference's
-op-by-op composition on the per-op kernels of this library (march_rays_train -> point_decode ->
-composite_rays_train with analytic backward) so autograd into the decoder weights keeps working.
+fused differentiable renderer (csrc/render_train.cu, gradient w.r.t. the code only); a trainable decoder (training,
+SURVEY.md §8 f2) raises.  `point_decode` / `point_density_decode` are one native launch (csrc/point_decode.cu).
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib as N
 from . import renderer as R
 from .activation import TruncExp
-from .raymarching import batch_composite_rays_train, batch_near_far_from_aabb, march_rays_train
 from .registry import MODULES, build_module
 from .shencoder import SHEncoder
 
@@ -147,61 +144,47 @@ class TriPlaneDecoder(VolumeRenderer):
             self._blob = (key, R.pack_decoder_blob(self.decoder_params(), self.fused_variant(), self.sigmoid_saturation, self.aabb.device))
         return self._blob[1]
 
-    # ------------------------------------------------------------------ reference API: point decode (module path)
-    def xyz_transform(self, xyz):
-        if self.flip_z:
-            xyz = torch.cat([xyz[..., :2], -xyz[..., 2:]], dim=-1)
-        xy, xz, yz = xyz[..., :2], xyz[..., ::2], xyz[..., 1:]
-        if xyz.dim() == 2:
-            return torch.stack([xy, xz, yz], dim=0).unsqueeze(1)
-        if xyz.dim() == 3:
-            num_scenes, num_points, _ = xyz.size()
-            return torch.stack([xy, xz, yz], dim=1).reshape(num_scenes * 3, 1, num_points, 2)
-        raise ValueError
-
+    # ------------------------------------------------------------------ reference API: stand-alone point decode
     def point_decode(self, xyzs, dirs, code, density_only=False):
-        """triplane_decoder.py:119-179 (differentiable module path used by the train branch and by external callers)."""
-        num_scenes, _, n_channels, h, w = code.size()
-        if self.code_dropout is not None:
-            code = self.code_dropout(code.reshape(num_scenes * 3, n_channels, h, w)).reshape(num_scenes, 3, n_channels, h, w)
-        if isinstance(xyzs, torch.Tensor):
-            assert xyzs.dim() == 3
-            num_points = xyzs.size(-2)
-            point_code = F.grid_sample(code.reshape(num_scenes * 3, -1, h, w), self.xyz_transform(xyzs), mode=self.interp_mode,
-                                       padding_mode='border', align_corners=False).reshape(num_scenes, 3, -1, num_points)
-            point_code = point_code.permute(0, 3, 2, 1).reshape(num_scenes * num_points, -1)
-            num_points = [num_points] * num_scenes
-        else:
-            num_points, point_code = [], []
-            for code_single, xyzs_single in zip(code, xyzs):
-                n = xyzs_single.size(-2)
-                pc = F.grid_sample(code_single, self.xyz_transform(xyzs_single), mode=self.interp_mode, padding_mode='border',
-                                   align_corners=False).squeeze(-2)
-                point_code.append(pc.permute(2, 1, 0).reshape(n, -1))
-                num_points.append(n)
-            point_code = torch.cat(point_code, dim=0) if len(point_code) > 1 else point_code[0]
-        base_x = self.base_net(point_code)
-        base_x_act = self.base_activation(base_x)
-        sigmas = self.density_net(base_x_act).squeeze(-1)
-        if density_only:
-            return sigmas, None, num_points
-        if self.use_dir_enc:
-            dirs = torch.cat(dirs, dim=0) if num_scenes > 1 else dirs[0]
-            sh_enc = self.dir_encoder(dirs)
-            if self.dir_net is not None:
-                color_in = self.base_activation(base_x + self.dir_net(sh_enc))
-            else:
-                color_in = torch.cat([base_x_act, sh_enc], dim=-1)
-        else:
-            color_in = base_x_act
-        rgbs = self.color_net(color_in)
-        if self.sigmoid_saturation > 0:
-            rgbs = rgbs * (1 + self.sigmoid_saturation * 2) - self.sigmoid_saturation
-        return sigmas, rgbs, num_points
+        """sigma (and rgb) at arbitrary points: the call contract of triplane_decoder.py:119-179 --
+        xyzs: tensor [B,P,3] or a list of B tensors [P_i,3]; dirs: list of B tensors [P_i,3] (or one tensor [B,P,3]), unused when
+        `density_only`; code [B,3,C,H,W]  ->  (sigmas [sum P_i], rgbs [sum P_i,3] | None, [P_0, ..., P_{B-1}]).
+        One native launch (csrc/point_decode.cu); inference only -- the differentiable decode lives inside the fused
+        train-branch renderer (csrc/render_train.cu)."""
+        if torch.is_grad_enabled() and (code.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError('TriPlaneDecoder.point_decode is forward-only; gradients w.r.t. the code flow through the fused '
+                                      'differentiable renderer (decoder.forward in train mode), decoder-weight gradients are SURVEY.md §8 f2')
+        if self.code_dropout is not None and self.training:
+            raise NotImplementedError('code_dropout > 0 is unused by every reference config and not built')
+        N.require_cuda(code)
+        variant = self.fused_variant()
+        pts = [xyzs[i] for i in range(len(xyzs))] if not isinstance(xyzs, torch.Tensor) else list(xyzs.unbind(0))
+        if len(pts) != code.size(0):
+            raise ValueError(f'{len(pts)} point sets for {code.size(0)} scenes')
+        counts = [int(p.shape[-2]) for p in pts]
+        flat_xyz = torch.cat([p.reshape(-1, 3) for p in pts], dim=0).contiguous().float()
+        total = flat_xyz.shape[0]
+        offsets = torch.tensor([0] + [sum(counts[:i + 1]) for i in range(len(counts))], dtype=torch.int64).to(code.device, non_blocking=True)
+        flat_dir = None
+        if not density_only:
+            if not self.use_dir_enc:
+                raise NotImplementedError('decoders without direction encoding are unused by the reference configs and not built')
+            ds = list(dirs.unbind(0)) if isinstance(dirs, torch.Tensor) else list(dirs)
+            flat_dir = torch.cat([d.reshape(-1, 3) for d in ds], dim=0).contiguous().float()
+            if flat_dir.shape[0] != total:
+                raise ValueError('xyzs and dirs disagree on the number of points')
+        sigmas = torch.empty(total, dtype=torch.float32, device=code.device)
+        rgbs = None if density_only else torch.empty(total, 3, dtype=torch.float32, device=code.device)
+        planes = R.pack_planes(code.detach(), variant)
+        N.check(N.lib().ssdnerf_point_decode(N.c_int(variant), N.ptr(planes), N.c_u32(code.shape[-2]), N.c_u32(code.shape[-1]),
+                                             N.ptr(self.packed_blob()), N.ptr(flat_xyz), N.ptr(flat_dir), N.ptr(offsets), N.c_u32(len(counts)),
+                                             N.ctypes.c_ulonglong(total), N.ptr(sigmas), N.ptr(rgbs), N.stream_ptr()))
+        return sigmas, rgbs, counts
 
     def point_density_decode(self, xyzs, code, **kwargs):
-        sigmas, _, num_points = self.point_decode(xyzs, None, code, density_only=True, **kwargs)
-        return sigmas, num_points
+        """triplane_decoder.py:181-184"""
+        sigmas, _, counts = self.point_decode(xyzs, None, code, density_only=True, **kwargs)
+        return sigmas, counts
 
     # ------------------------------------------------------------------ forward
     def forward(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma=0, perturb=False, T_thresh=1e-4, return_loss=False):
@@ -242,8 +225,6 @@ class TriPlaneDecoder(VolumeRenderer):
         return dict(weights_sum=list(out['weights_sum']), depth=list(out['depth']), image=list(out['image']))
 
     def _fused_train_ok(self, rays_o, code, grid_size):
-        if not getattr(self, 'fused_train', True):      # set False to force the per-op composition (A/B tests)
-            return False
         if self.code_dropout is not None or any(p.requires_grad for p in self.parameters()):
             return False
         if not isinstance(rays_o, torch.Tensor) and len({r.size(0) for r in rays_o}) != 1:
@@ -279,24 +260,12 @@ class TriPlaneDecoder(VolumeRenderer):
         return dict(weights_sum=ws, depth=depth, image=image)
 
     def _forward_train(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh):
+        """base_volume_renderer.py:59-77.  The train branch exists as ONE fused differentiable op for the frozen shipped-config decoder
+        (guidance, code optimisation: diffusion_nerf.py:273,358).  A trainable decoder needs decoder-weight gradients (training,
+        SURVEY.md §8 f2), which this build does not have: it fails loudly rather than falling back to a PyTorch composition.  The
+        reference's per-op kernels stay available one by one in `ssdnerf_b200.raymarching` (march_rays_train, composite_rays_train)."""
         if self._fused_train_ok(rays_o, code, grid_size):
             return self._forward_train_fused(rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh)
-        num_scenes = len(rays_o)
-        if isinstance(grid_size, int):
-            grid_size = [grid_size] * num_scenes
-        if isinstance(dt_gamma, (int, float)):
-            dt_gamma = [float(dt_gamma)] * num_scenes
-        nears, fars = batch_near_far_from_aabb(rays_o, rays_d, self.aabb, self.min_near)
-        xyzs, dirs, deltas, rays = [], [], [], []
-        for ro, rd, bf, ne, fa, gs, dtg in zip(rays_o, rays_d, density_bitfield, nears, fars, grid_size, dt_gamma):
-            noi = None
-            if isinstance(perturb, torch.Tensor):
-                noi, per = perturb.reshape(num_scenes, -1)[len(rays)], True
-            else:
-                per = bool(perturb)
-            x, d, de, r = march_rays_train(ro, rd, self.bound, bf, 1, gs, ne, fa, perturb=per, align=128, force_all_rays=True,
-                                           dt_gamma=float(dtg), max_steps=self.max_steps, noises=noi)
-            xyzs.append(x); dirs.append(d); deltas.append(de); rays.append(r)
-        sigmas, rgbs, num_points = self.point_decode(xyzs, dirs, code)
-        weights_sum, depth, image = batch_composite_rays_train(sigmas, rgbs, deltas, rays, num_points, T_thresh)
-        return dict(weights_sum=weights_sum, depth=depth, image=image)
+        raise NotImplementedError(
+            'TriPlaneDecoder train branch: only the frozen shipped-config decoder (3x6-channel triplanes, hidden 64, dir_net) with equal ray '
+            'counts per scene is built (fused differentiable renderer); decoder-weight gradients are SURVEY.md §8 f2')

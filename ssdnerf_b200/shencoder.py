@@ -1,66 +1,70 @@
-"""Mirror of the reference's ``lib.ops.shencoder`` (lib/ops/shencoder/sphere_harmonics.py:15-87).
+"""Spherical-harmonics direction encoding as a stand-alone op (C ABI §1: ssdnerf_sh_encode_forward / _backward).
 
-The fused renderer evaluates SH16 once per RAY in registers (ssdnerf_b200/csrc/common.cuh `sh16`); this
-module is the stand-alone op for callers that use ``SHEncoder`` directly (e.g. TriPlaneDecoder.point_decode).
+API contract kept from the reference's ``lib.ops.shencoder`` (lib/ops/shencoder/sphere_harmonics.py:61-87): the module name
+``SHEncoder(input_dim=3, degree=4)``, its ``output_dim`` attribute, ``forward(inputs, size=1)`` and the functional
+``sh_encode(inputs, degree, calc_grad_inputs)``.  The fused renderers never call this: they evaluate the 16 basis values once
+per RAY in registers (csrc/common.cuh `sh16`); this op serves direct users of the encoder.
 """
 import torch
 import torch.nn as nn
-from torch.autograd import Function
 
 from . import _lib as N
 
+MAX_DEGREE = 4
 
-class _sh_encoder(Function):
-    @staticmethod
-    def forward(ctx, inputs, degree, calc_grad_inputs=False):
-        N.require_cuda(inputs)
-        inputs = inputs.contiguous().float()
-        B, input_dim = inputs.shape
-        output_dim = degree ** 2
-        outputs = torch.empty(B, output_dim, dtype=torch.float32, device=inputs.device)
-        dy_dx = torch.empty(B, input_dim * output_dim, dtype=torch.float32, device=inputs.device) if calc_grad_inputs \
-            else torch.empty(1, dtype=torch.float32, device=inputs.device)
-        N.check(N.lib().ssdnerf_sh_encode_forward(N.ptr(inputs), N.ptr(outputs), N.c_u32(B), N.c_u32(input_dim),
-                                                  N.c_u32(degree), N.c_int(int(calc_grad_inputs)), N.ptr(dy_dx),
-                                                  N.stream_ptr()))
-        ctx.save_for_backward(inputs, dy_dx)
-        ctx.dims = [B, input_dim, degree]
-        ctx.calc_grad_inputs = calc_grad_inputs
-        return outputs
+
+def _launch_forward(dirs, degree, want_jacobian):
+    """dirs fp32 [M,3] on the GPU -> (basis [M, degree^2], jacobian [M, 3*degree^2] | 1-element placeholder)"""
+    M = dirs.shape[0]
+    n_basis = degree * degree
+    basis = dirs.new_empty(M, n_basis)
+    jac = dirs.new_empty(M, 3 * n_basis) if want_jacobian else dirs.new_empty(1)
+    N.check(N.lib().ssdnerf_sh_encode_forward(N.ptr(dirs), N.ptr(basis), N.c_u32(M), N.c_u32(3), N.c_u32(degree),
+                                              N.c_int(1 if want_jacobian else 0), N.ptr(jac), N.stream_ptr()))
+    return basis, jac
+
+
+class _SHBasis(torch.autograd.Function):
+    """basis values with an optional gradient w.r.t. the directions (the kernel stores d basis / d dir in forward)"""
 
     @staticmethod
-    def backward(ctx, grad):
-        if not ctx.calc_grad_inputs:
+    def forward(ctx, dirs, degree, want_dir_grad):
+        N.require_cuda(dirs)
+        dirs = dirs.contiguous().float()
+        basis, jac = _launch_forward(dirs, degree, want_dir_grad)
+        ctx.degree, ctx.want_dir_grad = degree, want_dir_grad
+        if want_dir_grad:
+            ctx.save_for_backward(dirs, jac)
+        return basis
+
+    @staticmethod
+    def backward(ctx, grad_basis):
+        if not ctx.want_dir_grad:
             return None, None, None
-        grad = grad.contiguous().float()
-        inputs, dy_dx = ctx.saved_tensors
-        B, input_dim, degree = ctx.dims
-        grad_inputs = torch.zeros_like(inputs)
-        N.check(N.lib().ssdnerf_sh_encode_backward(N.ptr(grad), N.ptr(inputs), N.c_u32(B), N.c_u32(input_dim),
-                                                   N.c_u32(degree), N.ptr(dy_dx), N.ptr(grad_inputs), N.stream_ptr()))
-        return grad_inputs, None, None
+        dirs, jac = ctx.saved_tensors
+        grad_dirs = torch.zeros_like(dirs)
+        N.check(N.lib().ssdnerf_sh_encode_backward(N.ptr(grad_basis.contiguous().float()), N.ptr(dirs), N.c_u32(dirs.shape[0]), N.c_u32(3),
+                                                   N.c_u32(ctx.degree), N.ptr(jac), N.ptr(grad_dirs), N.stream_ptr()))
+        return grad_dirs, None, None
 
 
-sh_encode = _sh_encoder.apply
+def sh_encode(inputs, degree, calc_grad_inputs=False):
+    return _SHBasis.apply(inputs, degree, calc_grad_inputs)
 
 
 class SHEncoder(nn.Module):
-    """sphere_harmonics.py:61-87 (degree <= 4 here; the model uses 4 -> 16 features)."""
-
     def __init__(self, input_dim=3, degree=4):
         super().__init__()
-        self.input_dim = input_dim
-        self.degree = degree
-        self.output_dim = degree ** 2
-        assert self.input_dim == 3, 'SH encoder only support input dim == 3'
-        assert 0 < self.degree <= 4, 'this build supports SH degree in [1, 4]'
+        if input_dim != 3:
+            raise ValueError('SH encoder only support input dim == 3')
+        if not 1 <= degree <= MAX_DEGREE:
+            raise ValueError(f'this build evaluates SH up to degree {MAX_DEGREE} (the model uses 4 -> 16 features), got {degree}')
+        self.input_dim, self.degree, self.output_dim = input_dim, degree, degree * degree
 
-    def __repr__(self):
-        return f'SHEncoder: input_dim={self.input_dim} degree={self.degree}'
+    def extra_repr(self):
+        return f'input_dim={self.input_dim}, degree={self.degree}'
 
     def forward(self, inputs, size=1):
-        inputs = inputs / size
-        prefix_shape = list(inputs.shape[:-1])
-        inputs = inputs.reshape(-1, self.input_dim)
-        outputs = sh_encode(inputs, self.degree, inputs.requires_grad)
-        return outputs.reshape(prefix_shape + [self.output_dim])
+        flat = (inputs / size).reshape(-1, self.input_dim)
+        out = sh_encode(flat, self.degree, flat.requires_grad)
+        return out.reshape(*inputs.shape[:-1], self.output_dim)

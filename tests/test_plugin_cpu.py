@@ -103,11 +103,11 @@ def test_guidance_host_logic():
 
 
 def test_guided_sampling_contract():
-    """grad_through_unet=True (the reference default) needs the UNet backward and must say so; CPU tensors never reach a fallback"""
+    """guidance through the denoiser runs on the native UNet (forward + input-gradient pass): CPU tensors never reach a fallback"""
     cfg = S.Config.fromfile(os.path.join(ROOT, 'configs', 'cars_uncond_b200.py'))
     m = S.build_model(cfg.model, test_cfg=dict(cfg.test_cfg))
     d = m.diffusion
-    with pytest.raises(NotImplementedError, match='grad_through_unet'):
+    with pytest.raises(S._lib.SSDNeRFNativeError):
         d.pred_x_0(torch.zeros(1, 18, 128, 128), torch.tensor([10]), grad_guide_fn=lambda x: x.sum(), cfg=dict(clip_range=[-2, 2]))
     with pytest.raises(S._lib.SSDNeRFNativeError):
         m.val_guide(dict(cond_imgs=torch.zeros(1, 1, 8, 8, 3), cond_intrinsics=torch.ones(1, 1, 4), cond_poses=torch.eye(4).expand(1, 1, 4, 4)))

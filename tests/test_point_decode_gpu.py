@@ -1,0 +1,54 @@
+"""TriPlaneDecoder.point_decode / point_density_decode (one native launch, csrc/point_decode.cu) vs the oracle's restatement of
+triplane_decoder.py:104-184.  fp32 MLP with fast intrinsics (ex2 / rcp approx): rtol 2e-4 / atol 2e-5 like the fused P renderer."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_port as rp
+
+pytestmark = pytest.mark.gpu
+
+
+def _decoder(params, cuda):
+    import ssdnerf_b200 as S
+    dec = S.build_module(dict(type='TriPlaneDecoder', base_layers=[18, 64], density_layers=[64, 1], color_layers=[64, 3], use_dir_enc=True,
+                              dir_layers=[16, 64], max_steps=256))
+    sd = dec.state_dict(); sd.update(params); dec.load_state_dict(sd)
+    return dec.to(cuda).eval()
+
+
+@pytest.mark.parametrize('ragged', [False, True])
+def test_point_decode_matches_oracle(cuda, ragged):
+    g = torch.Generator().manual_seed(3)
+    B = 3
+    code = (torch.randn(B, 3, 6, 128, 128, generator=g) * 0.7).clamp(-2, 2)
+    params = rp.make_decoder_params('P', 7)
+    dec = _decoder(params, cuda)
+    counts = [257, 1, 1000] if ragged else [300] * B
+    # points inside and OUTSIDE [-1, 1]^3 (border clamp of grid_sample), unit directions
+    xyzs = [torch.rand(n, 3, generator=g) * 2.4 - 1.2 for n in counts]
+    dirs = [torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) for n in counts]
+    if ragged:
+        sig, rgb, num = dec.point_decode([x.to(cuda) for x in xyzs], [d.to(cuda) for d in dirs], code.to(cuda))
+    else:
+        sig, rgb, num = dec.point_decode(torch.stack(xyzs).to(cuda), [d.to(cuda) for d in dirs], code.to(cuda))
+    assert num == counts and sig.shape == (sum(counts),) and rgb.shape == (sum(counts), 3)
+    ref_s, ref_c = zip(*[rp.point_decode(params, xyzs[b], dirs[b], code[b]) for b in range(B)])
+    np.testing.assert_allclose(sig.cpu().numpy(), torch.cat(ref_s).numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(rgb.cpu().numpy(), torch.cat(ref_c).numpy(), rtol=2e-4, atol=2e-5)
+    sd, nd = dec.point_density_decode([x.to(cuda) for x in xyzs], code.to(cuda))
+    assert nd == counts
+    np.testing.assert_allclose(sd.cpu().numpy(), sig.cpu().numpy(), rtol=0, atol=0)       # same kernel, density-only path
+
+
+def test_point_decode_refuses_gradients_and_trainable_decoder(cuda):
+    params = rp.make_decoder_params('P', 7)
+    dec = _decoder(params, cuda)
+    code = torch.zeros(1, 3, 6, 128, 128, device=cuda, requires_grad=True)
+    x = torch.zeros(1, 4, 3, device=cuda)
+    with pytest.raises(NotImplementedError):
+        dec.point_decode(x, [x[0]], code)
+    dec.train()
+    dec.requires_grad_(True)            # trainable decoder: the train branch fails loudly (no PyTorch composition in the product)
+    with pytest.raises(NotImplementedError):
+        dec(torch.zeros(1, 8, 3, device=cuda), torch.ones(1, 8, 3, device=cuda), code.detach(), torch.zeros(1, 64 ** 3 // 8, dtype=torch.uint8, device=cuda), 64)

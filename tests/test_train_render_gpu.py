@@ -5,6 +5,8 @@ library's per-op composition (march_rays_train -> point_decode -> composite_rays
 reference's own (tests/test_ref_gpu.py).  Per-ray sample counts are integers: exact.
 Backward (d loss / d code): vs float64 autograd of the oracle chain, relative L2 <= 1e-3; vs per-op autograd relative L2 <= 1e-4
 (both scatter with fp32 atomics, so not bit-identical)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -13,6 +15,7 @@ from oracle import render_port as rp
 from oracle import train_port as tp
 from oracle import unet_port as up
 from tests.common import spiral_poses
+from tests.per_op_train import per_op_train_render
 
 pytestmark = pytest.mark.gpu
 
@@ -84,11 +87,9 @@ def test_train_forward_vs_oracle_and_per_op(cuda, T_thresh):
         np.testing.assert_allclose(out['depth'][b].cpu().numpy(), depth.numpy(), rtol=2e-4, atol=1e-4)
         n_break += int((ws > 1 - T_thresh).sum())
     assert T_thresh < 1e-3 or n_break > 20                               # the early-termination branch is exercised
-    # per-op composition of this library (same march kernel as the reference, torch decode)
-    dec = _decoder(params, cuda)
-    dec.fused_train = False
+    # per-op composition (tests/per_op_train.py: same march / composite kernels as the reference, torch decode)
     with torch.no_grad():
-        ref = dec(rays_o.to(cuda), rays_d.to(cuda), code.to(cuda), bft, 64, dt_gamma=dt_gamma.tolist(), perturb=noises.to(cuda), T_thresh=T_thresh)
+        ref = per_op_train_render(params, rays_o.to(cuda), rays_d.to(cuda), code.to(cuda), bft, dt_gamma.tolist(), noises.to(cuda), T_thresh=T_thresh)
     for k in ('weights_sum', 'image'):
         np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].cpu().numpy(), **TOL_P)
     np.testing.assert_allclose(out['depth'].cpu().numpy(), ref['depth'].cpu().numpy(), rtol=2e-4, atol=1e-4)
@@ -112,9 +113,11 @@ def test_train_backward_vs_oracle_and_per_op(cuda, T_thresh):
     grads = {}
     for fused in (True, False):
         dec = _decoder(params, cuda)
-        dec.fused_train = fused
         c = code.to(cuda).requires_grad_(True)
-        out = dec(rays_o.to(cuda), rays_d.to(cuda), c, bft, 64, dt_gamma=dt_gamma.tolist(), perturb=noises.to(cuda), T_thresh=T_thresh)
+        if fused:
+            out = dec(rays_o.to(cuda), rays_d.to(cuda), c, bft, 64, dt_gamma=dt_gamma.tolist(), perturb=noises.to(cuda), T_thresh=T_thresh)
+        else:
+            out = per_op_train_render(params, rays_o.to(cuda), rays_d.to(cuda), c, bft, dt_gamma.tolist(), noises.to(cuda), T_thresh=T_thresh)
         loss = (out['image'] * g_img.to(cuda)).sum() + (out['weights_sum'] * g_ws.to(cuda)).sum()
         grads[fused], = torch.autograd.grad(loss, c)
     assert float(grad_ref.abs().max()) > 0
@@ -151,10 +154,17 @@ def test_loss_fused_vs_oracle_and_module_composition(cuda):
     bft = torch.from_numpy(bf).to(cuda)
     res = {}
     for fused in (True, False):
-        dec.fused_train = fused
         c = code.to(cuda).requires_grad_(True)
-        rgb, loss, ld = model.loss(dec, c, bft, target.to(cuda), rays_o.to(cuda), rays_d.to(cuda), dt_gamma.to(cuda) if fused else dt_gamma.tolist(),
-                                   scale_num_ray=n, cfg=cfg, perturb=noises.to(cuda))
+        if fused:
+            rgb, loss, ld = model.loss(dec, c, bft, target.to(cuda), rays_o.to(cuda), rays_d.to(cuda), dt_gamma.to(cuda), scale_num_ray=n, cfg=cfg,
+                                       perturb=noises.to(cuda))
+        else:       # base_nerf.py:276-296 composed from the per-op render + the loss modules
+            out = per_op_train_render(params, rays_o.to(cuda), rays_d.to(cuda), c, bft, dt_gamma.tolist(), noises.to(cuda))
+            rgb = out['image'] + 1.0 * (1 - out['weights_sum'].unsqueeze(-1))
+            scale = 1 - math.exp(-cfg['loss_coef'] * n)
+            pl = model.pixel_loss(rgb, target.to(cuda)) * (scale * 3)
+            rl = model.reg_loss(c)
+            loss, ld = pl + rl, dict(pixel_loss=pl, reg_loss=rl)
         grad, = torch.autograd.grad(loss * B, c)
         res[fused] = (float(loss), grad, rgb.detach(), {k: float(v) for k, v in ld.items()})
     loss_ref, grad_ref, rgb_ref = tp.render_loss_grad(params, code, rays_o.numpy(), rays_d.numpy(), target.numpy(), bf, noises=noises.numpy(),
