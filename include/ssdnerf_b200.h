@@ -323,6 +323,46 @@ SSDNERF_API int ssdnerf_ddim_update(float* x_t, const float* v, uint32_t B, uint
 SSDNERF_API int ssdnerf_step_counter(int* step_ptr, int value, int set, void* stream);
 SSDNERF_API int ssdnerf_select_row(const float* table, uint32_t row_elems, const int* step_ptr, float* dst, uint32_t copies, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 4b. UNet input-gradient pass (frozen weights): the memory-bound kernels between the data-gradient GEMMs.
+ *     replaces: torch.autograd through the denoiser in lib/models/diffusions/gaussian_diffusion.py:193-216
+ *       (guidance with grad_through_unet=True) and lib/models/autodecoders/diffusion_nerf.py:356-372 (val_optim:
+ *       loss.backward() of the diffusion prior w.r.t. the code).  Convolution / linear data gradients reuse ssdnerf_gemm_f16 on
+ *       transposed, tap-flipped weights.  Gradients are fp16 NHWC under a device-side loss scale.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ssdnerf_gn_bwd_args {
+    const void* x1; uint32_t C1;           /* raw GroupNorm input, source 1: fp16 [B][HW][C1] */
+    const void* x2; uint32_t C2;           /* source 2 of a channel concat or NULL */
+    uint32_t B, HW, groups;
+    const float* stats; const float* stats2; int quad_stats;   /* forward statistics as for ssdnerf_gn_apply / ssdnerf_gn_apply_q */
+    const float* gamma; const float* beta; /* [C1+C2] */
+    const float* scale_shift; long long ss_batch_stride;       /* NormWithEmbedding (1 + scale, shift) rows or NULL */
+    float eps; int do_silu;
+    const void* dy;                        /* gradient w.r.t. the (SiLU'd) normalised output, fp16 [B][HW][C1+C2] */
+    const void* add;                       /* optional gradient added to the result (shortcut / residual), fp16 [B][HW][C1+C2] */
+    float* group_sums;                     /* scratch [B][groups][2] */
+    void* dx1; void* dx2;                  /* out: fp16 [B][HW][C1], [B][HW][C2] */
+} ssdnerf_gn_bwd_args;
+SSDNERF_API int ssdnerf_gn_bwd(const ssdnerf_gn_bwd_args* args, void* stream);
+/* dS = P * (dP - rowsum(P * dP)): softmax backward over attention rows; P fp16, dP fp32, dS fp16, [rows][T] */
+SSDNERF_API int ssdnerf_softmax_bwd_rows(const void* P, const float* dP, uint32_t rows, uint32_t T, void* dS, void* stream);
+/* n2 x n1 batched fp16 transposes: dst[((b2*n1 + b1)*cols + c)*rows + r] = src[b2*stride2 + b1*stride1 + r*row_stride + c] (elements) */
+SSDNERF_API int ssdnerf_transpose_f16(const void* src, void* dst, uint32_t rows, uint32_t cols, long long row_stride, long long stride1,
+                                      uint32_t n1, long long stride2, uint32_t n2, void* stream);
+/* data gradient of ssdnerf_im2col_s2 (+ optional add [B][H][W][C]): dcol fp16 [B][H/2][W/2][9C] -> dx fp16 [B][H][W][C] */
+SSDNERF_API int ssdnerf_col2im_s2(const void* dcol, uint32_t B, uint32_t H, uint32_t W, uint32_t C, const void* add, void* dx, void* stream);
+/* data gradient of ssdnerf_upsample2x: dup fp16 [B][2H][2W][C] -> dx fp16 [B][H][W][C] */
+SSDNERF_API int ssdnerf_sum2x2(const void* dup, uint32_t B, uint32_t H, uint32_t W, uint32_t C, void* dx, void* stream);
+/* dst += src over n fp16 elements (n % 8 == 0) */
+SSDNERF_API int ssdnerf_add_f16(void* dst, const void* src, unsigned long long n, void* stream);
+/* loss scale of an incoming gradient: scale[0] = target / max|g| (1 when g == 0), scale[1] = 1 / scale[0]; g fp32 [n] */
+SSDNERF_API int ssdnerf_grad_scale(const float* g, unsigned long long n, float target, float* scale, void* stream);
+/* g fp32 [B][C][H][W] * scale[0] -> fp16 [B][H][W][Cpad];  dx fp32 [B][H][W][Cpad] * scale[1] -> fp32 [B][C][H][W] */
+SSDNERF_API int ssdnerf_grad_nchw_to_nhwc_f16(const float* g, uint32_t B, uint32_t C, uint32_t H, uint32_t W, uint32_t Cpad, const float* scale,
+                                              void* out, void* stream);
+SSDNERF_API int ssdnerf_grad_nhwc_to_nchw_f32(const float* dx, uint32_t B, uint32_t C, uint32_t H, uint32_t W, uint32_t Cpad, const float* scale,
+                                              float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,17 @@ def stream_ptr(device=None):
 
 
 def require_cuda(*tensors):
+    """Every native op launches on the CURRENT device's current stream (`stream_ptr`), so its tensors must live on that device:
+    a model on cuda:1 needs `torch.cuda.set_device(1)` (or a `torch.cuda.device(1)` block) around its calls -- enforced here
+    instead of launching device-0 kernels on device-1 pointers."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise SSDNeRFNativeError('ssdnerf_b200 ops run on CUDA tensors only (no CPU fallback)')
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise SSDNeRFNativeError(f'tensor on cuda:{t.device.index} but the current device is cuda:{cur}: the library launches on the '
+                                     'current device (one GPU per process, or wrap the call in torch.cuda.device(...))')

@@ -151,7 +151,7 @@ class TriPlaneDecoder(VolumeRenderer):
         `density_only`; code [B,3,C,H,W]  ->  (sigmas [sum P_i], rgbs [sum P_i,3] | None, [P_0, ..., P_{B-1}]).
         One native launch (csrc/point_decode.cu); inference only -- the differentiable decode lives inside the fused
         train-branch renderer (csrc/render_train.cu)."""
-        if torch.is_grad_enabled() and (code.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (code.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             raise NotImplementedError('TriPlaneDecoder.point_decode is forward-only; gradients w.r.t. the code flow through the fused '
                                       'differentiable renderer (decoder.forward in train mode), decoder-weight gradients are SURVEY.md §8 f2')
         if self.code_dropout is not None and self.training:

@@ -21,6 +21,107 @@ from .registry import MODULES, build_module
 
 
 @MODULES.register_module()
+class UniformTimeStepSampler:
+    """mmgen.models.diffusions.sampler.UniformTimeStepSampler [mmgen-memory]: t ~ Categorical(prob) drawn with NumPy on the host"""
+
+    def __init__(self, num_timesteps, **kwargs):
+        self.num_timesteps = num_timesteps
+        self.prob = [1 / num_timesteps for _ in range(num_timesteps)]
+
+    def sample(self, batch_size):
+        return torch.from_numpy(np.random.choice(self.num_timesteps, size=(batch_size,), p=self.prob)).long()
+
+    def __call__(self, batch_size):
+        return self.sample(batch_size)
+
+
+@MODULES.register_module()
+class UniformTimeStepSamplerMod(UniformTimeStepSampler):
+    """lib/models/diffusions/sampler.py:7-11"""
+
+
+@MODULES.register_module()
+class SNRWeightedTimeStepSampler(UniformTimeStepSampler):
+    """lib/models/diffusions/sampler.py:14-46: per-timestep loss weight from the signal-to-noise ratio (+ optional importance sampling)"""
+
+    def __init__(self, num_timesteps, mean, std, mode, power=1, min=-1, max=-1, bias=0, prob_power=0.0):
+        self.num_timesteps = num_timesteps
+        weight_x = (mean / std) ** (2 * power) + bias
+        if min > 0:
+            weight_x = weight_x.clip(min=min)
+        if max > 0:
+            weight_x = weight_x.clip(max=max)
+        mode = mode.upper()
+        if mode == 'EPS':
+            weight_raw = weight_x * (std / mean) ** 2
+        elif mode == 'START_X':
+            weight_raw = weight_x
+        elif mode == 'V':
+            weight_raw = weight_x * (std ** 2)
+        else:
+            raise AttributeError(f'unknown denoising mean mode {mode}')
+        prob = weight_raw ** prob_power
+        prob = prob / prob.sum()
+        self.weight = torch.from_numpy(weight_raw / (prob * self.num_timesteps)).to(torch.float)
+        self.prob = prob.tolist()
+
+
+@MODULES.register_module()
+class DDPMMSELossMod(nn.Module):
+    """lib/models/losses/ddpm_loss.py:12-131 on mmgen's DDPMLoss base [mmgen-memory]: per-sample 0.5 * MSE between the tensors named by
+    `data_info`, rescaled per timestep (`rescale_mode='timestep_weight'`: sampler.weight[t] * weight_scale), mean over the batch, divided
+    by the running `norm_factor` buffer when `scale_norm` (the buffer is part of released checkpoints)."""
+    _default_data_info = dict(pred='eps_t_pred', target='noise')
+
+    def __init__(self, rescale_mode=None, rescale_cfg=None, sampler=None, weight=None, weight_scale=1.0, log_cfgs=None, reduction='mean',
+                 data_info=None, loss_name='loss_ddpm_mse', scale_norm=False, momentum=0.001):
+        super().__init__()
+        assert reduction in ('mean', 'sum', 'none', 'flatmean')
+        self.rescale_mode, self.weight_scale, self.reduction, self.loss_name = rescale_mode, weight_scale, reduction, loss_name
+        self.data_info = dict(self._default_data_info if data_info is None else data_info)
+        if rescale_mode == 'timestep_weight':
+            w = weight if weight is not None else getattr(sampler, 'weight', None)
+            if w is None:
+                raise ValueError("rescale_mode='timestep_weight' needs `weight` or a sampler with a `weight` table")
+            self._t_weight = torch.as_tensor(w, dtype=torch.float).clone()
+        elif rescale_mode == 'constant':
+            self._t_weight = None
+            self._const = (rescale_cfg or {}).get('scale', 1.0)
+        elif rescale_mode is None:
+            self._t_weight = None
+        else:
+            raise NotImplementedError(f'rescale_mode {rescale_mode} is not used by the reference configs')
+        self.scale_norm, self.freeze_norm, self.momentum = scale_norm, False, momentum
+        if scale_norm:
+            self.register_buffer('norm_factor', torch.ones(1, dtype=torch.float))
+        self.log_vars = dict()
+
+    def forward(self, output_dict):
+        t = output_dict['timesteps']
+        pred, target = output_dict[self.data_info['pred']], output_dict[self.data_info['target']]
+        loss = (pred - target).square().flatten(1).mean(dim=1) * 0.5
+        if self.rescale_mode == 'timestep_weight':
+            loss = loss * self._t_weight.to(t.device)[t] * self.weight_scale
+        elif self.rescale_mode == 'constant':
+            loss = loss * self._const
+        self.log_vars = {self.loss_name: float(loss.detach().mean())}
+        loss = dict(mean=loss.mean, sum=loss.sum, flatmean=loss.mean, none=lambda: loss)[self.reduction]()
+        if self.scale_norm:
+            if self.training and not self.freeze_norm:
+                with torch.no_grad():
+                    nf = output_dict['x_0'].detach().square().mean()
+                    if torch.distributed.is_available() and torch.distributed.is_initialized():
+                        torch.distributed.all_reduce(nf)
+                        nf = nf / torch.distributed.get_world_size()
+                    self.norm_factor.lerp_(nf.to(self.norm_factor).reshape(1), self.momentum)
+            loss = loss / self.norm_factor
+        return loss
+
+
+MODULES.register_module(name='DDPMMSELoss', module=DDPMMSELossMod)      # the class default of gaussian_diffusion.py:18-21 (mmgen's own)
+
+
+@MODULES.register_module()
 class GaussianDiffusion(nn.Module):
 
     def __init__(self, denoising, ddpm_loss=None, betas_cfg=dict(type='cosine'), num_timesteps=1000, num_classes=0,
@@ -38,9 +139,14 @@ class GaussianDiffusion(nn.Module):
         self.betas_cfg = deepcopy(betas_cfg)
         self.train_cfg = deepcopy(train_cfg) if train_cfg is not None else dict()
         self.test_cfg = deepcopy(test_cfg) if test_cfg is not None else dict()
-        # training-only collaborators of the reference (loss, timestep sampler) are configuration we keep but do not build
-        self._ddpm_loss_cfg, self._timestep_sampler_cfg = deepcopy(ddpm_loss), deepcopy(timestep_sampler)
         self.prepare_diffusion_vars()
+        # gaussian_diffusion.py:54-62: the timestep sampler (carries the SNR loss weights) and the diffusion loss -- used at test time by
+        # val_optim / n_inverse_steps (the diffusion prior on the latent)
+        self.sampler = build_module(timestep_sampler if timestep_sampler is not None else dict(type='UniformTimeStepSampler'),
+                                    default_args=dict(num_timesteps=num_timesteps, mean=self.sqrt_alphas_bar, std=self.sqrt_one_minus_alphas_bar,
+                                                      mode=self.denoising_mean_mode))
+        loss_cfg = dict(ddpm_loss) if ddpm_loss is not None else dict(type='DDPMMSELoss')
+        self.ddpm_loss = build_module(loss_cfg, default_args=dict(sampler=self.sampler))
         self._graphs = {}
         self._graph_kernel_nodes = 0
 
@@ -111,7 +217,6 @@ class GaussianDiffusion(nn.Module):
             return sa * x_t - s1 * out
         raise AttributeError(f'Unknown denoising mean output type [{self.denoising_mean_mode}].')
 
-    @torch.no_grad()
     def pred_x_0(self, x_t, t, grad_guide_fn=None, concat_cond=None, cfg=dict(), update_denoising_output=False):
         """gaussian_diffusion.py:180-240.  With `grad_guide_fn` the guidance gradient is taken w.r.t. x_t THROUGH the denoiser
         (`grad_through_unet=True`, the reference default: the UNet's hand-written input-gradient pass, unet.py `_UNetInputGrad`)
@@ -131,7 +236,8 @@ class GaussianDiffusion(nn.Module):
         through = grad_guide_fn is not None and grad_through_unet
         if through:
             x_t = x_t.detach().requires_grad_(True)
-        with torch.set_grad_enabled(through):
+        # no guidance: the ambient autograd mode applies (forward_train differentiates the denoiser w.r.t. x_t for val_optim)
+        with torch.set_grad_enabled(through or (grad_guide_fn is None and torch.is_grad_enabled())):
             out = self.denoising(x_t, t, concat_cond=concat_cond)
             x_0 = self._x0_from_output(x_t, out, sa, s1)
             if grad_guide_fn is not None and clip_denoised:
@@ -340,8 +446,38 @@ class GaussianDiffusion(nn.Module):
         assert data.dim() == 4
         return self.sample_from_noise(data, **kwargs)
 
-    def forward_train(self, *args, **kwargs):
-        raise NotImplementedError('diffusion training is outside the accelerated hot paths (SURVEY.md §8 f2)')
+    def loss(self, denoising_output, x_0, noise, t, mean, std):
+        """gaussian_diffusion.py:404-421"""
+        mode = self.denoising_mean_mode.upper()
+        key = dict(EPS='eps_t_pred', START_X='x_0_pred', V='v_t_pred').get(mode)
+        if key is None:
+            raise AttributeError(f'Unknown denoising mean output type [{self.denoising_mean_mode}].')
+        loss_kwargs = {key: denoising_output, 'x_0': x_0, 'noise': noise, 'timesteps': t}
+        if mode == 'V':
+            loss_kwargs.update(v_t=mean * noise - std * x_0)
+        return self.ddpm_loss(loss_kwargs)
+
+    def forward_train(self, x_0, concat_cond=None, grad_guide_fn=None, cfg=dict(), x_t_detach=False, t=None, noise=None, **kwargs):
+        """gaussian_diffusion.py:423-450: diffusion loss of x_0 at sampled timesteps.  Differentiable w.r.t. x_0 (the UNet weights are
+        frozen constants in this build: test-time code optimisation; UNet training is SURVEY.md §8 f2).  `t` / `noise` may be injected."""
+        assert x_0.dim() == 4
+        if any(p.requires_grad for p in self.denoising.parameters()):
+            raise NotImplementedError('training the denoiser needs UNet weight gradients (SURVEY.md §8 f2); freeze it '
+                                      '(module_requires_grad(diffusion, False)) to differentiate w.r.t. the latent only')
+        num_batches = x_0.size(0)
+        if t is None:
+            t = self.sampler(num_batches)
+        t = t.to(x_0.device)
+        if noise is None:
+            noise = torch.randn_like(x_0)
+        x_t, mean, std = self.q_sample(x_0, t, noise)
+        if x_t_detach:
+            x_t = x_t.detach()
+        _, denoising_output = self.pred_x_0(x_t, t, grad_guide_fn=grad_guide_fn, concat_cond=concat_cond, cfg=cfg, update_denoising_output=True)
+        loss = self.loss(denoising_output, x_0, noise, t, mean, std)
+        log_vars = dict(self.ddpm_loss.log_vars)
+        log_vars.update(loss_ddpm_mse=float(loss.detach()))
+        return loss, log_vars
 
     def forward(self, data, return_loss=False, **kwargs):
         if return_loss:

@@ -20,8 +20,11 @@ from . import unet_ops as U
 from .registry import MODULES
 
 
+_GN_GROUPS = [32]      # construction-time GroupNorm group count (norm_cfg.num_groups), set by DenoisingUnetMod.__init__
+
+
 def _gn(c):
-    return nn.GroupNorm(32, c, eps=1e-5)
+    return nn.GroupNorm(_GN_GROUPS[0], c, eps=1e-5)
 
 
 class _ResBlockParams(nn.Module):
@@ -104,7 +107,7 @@ class DenoisingUnetMod(nn.Module):
         if not use_scale_shift_norm: unsupported.append('use_scale_shift_norm=False')
         if shortcut_kernel_size != 1: unsupported.append('shortcut_kernel_size != 1')
         if not (downsample_conv and upsample_conv): unsupported.append('pool / bare-interpolate resampling')
-        if norm_cfg.get('type') != 'GN' or norm_cfg.get('num_groups', 32) != 32: unsupported.append('norm other than GN32')
+        if norm_cfg.get('type') != 'GN': unsupported.append('norm other than GroupNorm')
         if act_cfg.get('type') != 'SiLU': unsupported.append('activation other than SiLU')
         if time_embedding_mode != 'sin': unsupported.append('time_embedding_mode != sin')
         if unsupported:
@@ -113,6 +116,8 @@ class DenoisingUnetMod(nn.Module):
         if not isinstance(channels_cfg, (list, tuple)):
             raise ValueError(f'Only support list for `channels_cfg`, receive {type(channels_cfg)}')
         self.num_classes, self.num_timesteps, self.use_rescale_timesteps = num_classes, num_timesteps, use_rescale_timesteps
+        self.num_groups = int(norm_cfg.get('num_groups', 32))
+        _GN_GROUPS[0] = self.num_groups
         self.out_channels = in_channels
         self.in_channels = in_channels
         self.concat_cond_channels = concat_cond_channels
@@ -163,6 +168,7 @@ class DenoisingUnetMod(nn.Module):
         self.out = nn.Module()
         self.out.conv = nn.Conv2d(cin, in_channels, 3, padding=1)       # mmcv ConvModule registers conv before the norm
         self.out.gn = _gn(cin)
+        _GN_GROUPS[0] = 32
         self._engine = None
         self._engine_key = None
 
@@ -181,9 +187,10 @@ class DenoisingUnetMod(nn.Module):
             t = t.float() * (1000.0 / self.num_timesteps)
         return self.time_embedding(t)
 
-    @torch.no_grad()
     def forward(self, x_t, t, label=None, concat_cond=None, return_noise=False):
-        """denoising.py:191-216. x_t [B,C,H,W] float; t [B] long. Returns fp32 [B,C,H,W]."""
+        """denoising.py:191-216. x_t [B,C,H,W] float; t [B] long. Returns fp32 [B,C,H,W].
+        Differentiable w.r.t. x_t (weights are treated as frozen constants): when autograd is recording and x_t requires a gradient
+        the forward keeps its activations and `backward` runs the hand-written input-gradient pass (`UNetEngine.backward_nhwc`)."""
         if label is not None:
             raise NotImplementedError('class-conditional embedding is not built (num_classes == 0 in every reference config)')
         N.require_cuda(x_t)
@@ -191,12 +198,38 @@ class DenoisingUnetMod(nn.Module):
         if self.concat_cond_channels > 0:
             h = torch.cat([h, concat_cond], dim=1)
         B = h.shape[0]
-        eng = self.engine(B, h.device)
         if t.dim() == 0 or t.numel() != B:
             t = t.expand(B)
-        eng.set_embedding(self.embedding(t.to(h.device)))
-        v = eng.forward_nchw(h.float().contiguous())
-        return v.permute(0, 3, 1, 2)[:, :self.out_channels].contiguous()
+        if torch.is_grad_enabled() and h.requires_grad:
+            if self.concat_cond_channels > 0:
+                raise NotImplementedError('input gradients with concat_cond are not built (unused by the shipped configs)')
+            return _UNetInputGrad.apply(h, self, t)
+        with torch.no_grad():
+            eng = self.engine(B, h.device)
+            eng.set_embedding(self.embedding(t.to(h.device)))
+            v = eng.forward_nchw(h.float().contiguous())
+            return v.permute(0, 3, 1, 2)[:, :self.out_channels].contiguous()
+
+
+class _UNetInputGrad(torch.autograd.Function):
+    """v = UNet(x_t, t) with d v / d x_t by the native input-gradient pass (weights frozen: guidance / val_optim never train them)."""
+
+    @staticmethod
+    def forward(ctx, x_t, module, t):
+        B = x_t.shape[0]
+        eng = module.engine(B, x_t.device)
+        eng.set_embedding(module.embedding(t.to(x_t.device)))
+        eng.load_input_nchw(x_t.detach().float().contiguous())
+        v = eng.forward_nhwc(save=True)
+        ctx.eng, ctx.token, ctx.C = eng, eng.fwd_token, module.out_channels
+        return v.permute(0, 3, 1, 2)[:, :module.out_channels].contiguous()
+
+    @staticmethod
+    def backward(ctx, grad_v):
+        eng = ctx.eng
+        if eng.fwd_token != ctx.token:
+            raise RuntimeError('UNet input gradient: the engine ran another forward before this backward (activations overwritten)')
+        return eng.backward_nchw(grad_v.contiguous().float()), None, None
 
 
 class UNetEngine:
@@ -206,6 +239,11 @@ class UNetEngine:
 
     def __init__(self, m: DenoisingUnetMod, batch, device):
         self.m, self.B, self.dev = m, batch, torch.device(device)
+        widths = sorted({m.base_channels * f for f in m.channel_factor_list} | {m.base_channels})
+        if m.num_groups != 32 or any(w % 64 for w in widths):
+            raise NotImplementedError(
+                f'native UNet engine: channel widths must be multiples of 64 with GroupNorm(32) (every paper config: base 128); got widths '
+                f'{widths}, {m.num_groups} groups (configs/new_cfgs/*_tiled.py builds and loads checkpoints but has no kernels yet)')
         self.flash_attention = True      # False: unfused scores -> softmax -> PV composition (A/B tests)
         # 128x128-level resblocks: GroupNorm + SiLU inside the conv kernel (csrc/conv_row2_gn.cu).  Opt-in: measured 98 us per 128->128 layer
         # against 22 + 59 us for the GroupNorm-apply pass + CTA-pair row-pair convolution (profiles/r01_gemm_pipeline_prof.txt)
@@ -268,6 +306,7 @@ class UNetEngine:
             off += 2 * d['cout']
         self.ss_total = off
         self.ss_cur = torch.zeros(batch, self.ss_total, dtype=torch.float32, device=dev)
+        self.saving, self.tape, self.fwd_token, self._bwd_packed = False, [], 0, False
         self.x_in = torch.zeros(batch, self.H, self.W, self.CPAD_IN, dtype=torch.float16, device=dev)
         self.v_out = torch.zeros(batch, self.H, self.W, self.out_conv['cout'], dtype=torch.float32, device=dev)
 
@@ -305,7 +344,8 @@ class UNetEngine:
         return t
 
     def _gn(self, x1, q1, x2, q2, gamma, beta, out, silu, ss_off=None):
-        """GroupNorm(32) over the channel concat of x1 (+x2) from the quad statistics their producers emitted"""
+        """GroupNorm(32) over the channel concat of x1 (+x2) from the quad statistics their producers emitted.
+        Leaves the statistics descriptor the backward needs in `self._last_stats` = (is_quad, stats1, stats2)."""
         B, H, W, C1 = x1.shape
         C2 = x2.shape[-1] if x2 is not None else 0
         L, s = N.lib(), N.stream_ptr()
@@ -320,7 +360,9 @@ class UNetEngine:
             N.check(L.ssdnerf_gn_apply(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(st),
                                        N.ptr(gamma), N.ptr(beta), ss, N.c_longlong(self.ss_total), N.c_f32(1e-5), N.c_int(int(silu)),
                                        N.ptr(out), s))
+            self._last_stats = (False, st, None)
             return out
+        self._last_stats = (True, q1, q2)
         N.check(L.ssdnerf_gn_apply_q(N.ptr(x1), N.c_u32(C1), N.ptr(x2), N.c_u32(C2), N.c_u32(B), N.c_u32(H * W), N.c_u32(32), N.ptr(q1),
                                      N.ptr(q2), N.ptr(gamma), N.ptr(beta), ss, N.c_longlong(self.ss_total), N.c_f32(1e-5),
                                      N.c_int(int(silu)), N.ptr(out), s))
@@ -337,6 +379,15 @@ class UNetEngine:
             sc = x
         qh1 = self._q(('h1', tag), cout)
         qo = self._q(('res_out', tag), cout)
+        if self.saving:       # keep what the input-gradient pass re-reads: raw inputs of both GroupNorms + their statistics
+            a = self._gn(x, qx, sk, qs, d['g1'], d['b1'], self._buf(('a', H, cin), (B, H, W, cin)), True)
+            st1 = self._last_stats
+            h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', tag), (B, H, W, cout)), qstats=qh1)
+            a2 = self._gn(h1, qh1, None, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
+            st2 = self._last_stats
+            out = U.conv3x3_f16(a2, d['w2'], cout, bias=d['c2b'], residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)), qstats=qo)
+            self.tape.append(dict(kind='res', d=d, x=x, sk=sk, st1=st1, h1=h1, st2=st2, out=out, tag=tag))
+            return out, qo
         if self.fused_gn_conv and W == 128 and cout == 128 and cin <= 384 and (cin // 32) % 4 == 0:
             # 128 x 128 level: GroupNorm apply + SiLU ride on the convolution's activation load path (csrc/conv_row2_gn.cu)
             h1 = U.conv3x3_gn_f16(x, qx, d['g1'], d['b1'], d['w1'], bias=d['c1b'], x2=sk, q2=qs,
@@ -358,7 +409,9 @@ class UNetEngine:
         ch = c // heads
         L, s = N.lib(), N.stream_ptr()
         xn = self._gn(x, qx, None, None, d['g'], d['b'], self._buf(('xn', T, c), (B, H, W, c)), False)
-        qkv = U.linear_f16(xn.view(B * T, c), d['wqkv'], bias=d['bqkv'], n=3 * c, out=self._buf(('qkv', T, c), (B * T, 3 * c)))
+        st = self._last_stats
+        qkv = U.linear_f16(xn.view(B * T, c), d['wqkv'], bias=d['bqkv'], n=3 * c,
+                           out=self._buf(('qkv', tag) if self.saving else ('qkv', T, c), (B * T, 3 * c)))
         if self.flash_attention and ch in (64, 128) and T % 64 == 0:
             o = U.flash_attn(qkv.view(B, T, 3 * c), heads, 1.0 / math.sqrt(ch), out=self._buf(('o', T, c), (B, T, c)))
         else:   # unfused composition (scores -> softmax -> P V), kept for head widths / lengths the fused kernel does not cover
@@ -369,8 +422,11 @@ class UNetEngine:
             N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
             o = U.attn_pv(P, vt, out=self._buf(('o', T, c), (B, T, c)))
         qo = self._q(('attn_out', tag), c)
-        return U.linear_f16(o.view(B * T, c), d['wproj'], bias=d['bproj'], residual=x.view(B * T, c), n=c,
-                            out=self._buf(('attn_out', tag), (B * T, c)), qstats=qo, stats_hw=T).view(B, H, W, c), qo
+        out = U.linear_f16(o.view(B * T, c), d['wproj'], bias=d['bproj'], residual=x.view(B * T, c), n=c,
+                           out=self._buf(('attn_out', tag), (B * T, c)), qstats=qo, stats_hw=T).view(B, H, W, c)
+        if self.saving:
+            self.tape.append(dict(kind='attn', d=d, x=x, st=st, qkv=qkv.view(B, T, 3 * c), out=out, tag=tag))
+        return out, qo
 
     def _down(self, d, x, tag):
         x, _ = x
@@ -379,8 +435,11 @@ class UNetEngine:
         N.check(N.lib().ssdnerf_im2col_s2(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(col), N.stream_ptr()))
         M = B * (H // 2) * (W // 2)
         qo = self._q(('down_out', tag), c)
-        return U.linear_f16(col.view(M, 9 * c), d['w'], bias=d['b'], n=c, out=self._buf(('down_out', tag), (M, c)), qstats=qo,
-                            stats_hw=(H // 2) * (W // 2)).view(B, H // 2, W // 2, c), qo
+        out = U.linear_f16(col.view(M, 9 * c), d['w'], bias=d['b'], n=c, out=self._buf(('down_out', tag), (M, c)), qstats=qo,
+                           stats_hw=(H // 2) * (W // 2)).view(B, H // 2, W // 2, c)
+        if self.saving:
+            self.tape.append(dict(kind='down', d=d, x=x, out=out, tag=tag))
+        return out, qo
 
     def _up(self, d, x, tag):
         x, _ = x
@@ -388,7 +447,10 @@ class UNetEngine:
         up = self._buf(('upx', H, c), (B, 2 * H, 2 * W, c))
         N.check(N.lib().ssdnerf_upsample2x(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(up), N.stream_ptr()))
         qo = self._q(('up_out', tag), c)
-        return U.conv3x3_f16(up, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)), qstats=qo), qo
+        out = U.conv3x3_f16(up, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)), qstats=qo)
+        if self.saving:
+            self.tape.append(dict(kind='up', d=d, x=x, out=out, tag=tag))
+        return out, qo
 
     def _run(self, layers, h, skip, tag):
         for li, (kind, d) in enumerate(layers):
@@ -405,13 +467,18 @@ class UNetEngine:
         return h
 
     # ------------------------------------------------------------------ forward
-    def forward_nhwc(self):
-        """x_in (self.x_in, fp16 NHWC padded) -> self.v_out (fp32 NHWC); all launches on the current stream, capture-safe."""
+    def forward_nhwc(self, save=False):
+        """x_in (self.x_in, fp16 NHWC padded) -> self.v_out (fp32 NHWC); all launches on the current stream, capture-safe.
+        save=True keeps every tensor the input-gradient pass re-reads (per-layer buffers instead of shared scratch) and records the tape."""
+        self.saving, self.tape = bool(save), []
+        self.fwd_token += 1
         self.qarena[:max(self.qoff, 1)].zero_()
         self._legacy_idx = 0
         q0 = self._q(('conv_in',), self.conv_in['cout'])
         h = (U.conv3x3_f16(self.x_in, self.conv_in['w'], self.conv_in['cout'], bias=self.conv_in['b'],
                            out=self._buf(('conv_in',), (self.B, self.H, self.W, self.conv_in['cout'])), qstats=q0), q0)
+        if self.saving:
+            self.tape.append(dict(kind='conv_in', out=h[0]))
         hs = [h]
         for i, layers in enumerate(self.in_seq):
             h = self._run(layers, h, None, ('in', i))
@@ -422,8 +489,149 @@ class UNetEngine:
         h, qh = h
         B, H, W, c = h.shape
         a = self._gn(h, qh, None, None, self.out_norm['g'], self.out_norm['b'], self._buf(('a', H, c), (B, H, W, c)), True)
+        if self.saving:
+            self.tape.append(dict(kind='out', x=h, st=self._last_stats))
         U.conv3x3_f16(a, self.out_conv['w'], self.out_conv['cout'], bias=self.out_conv['b'], out=self.v_out)
+        self.saving = False
         return self.v_out
+
+    # ------------------------------------------------------------------ input-gradient pass (weights frozen)
+    def _pack_backward_weights(self):
+        """transposed / tap-flipped fp16 copies of every weight, packed on first use (guidance and val_optim only)"""
+        m, dev = self.m, self.dev
+
+        def params(seq, mods):
+            for (kind, d), p in zip(seq, mods):
+                if kind == 'res':
+                    d['w1T'] = U.pack_conv_weight_dgrad(p.conv_1[2].weight).to(dev)
+                    d['w2T'] = U.pack_conv_weight_dgrad(p.conv_2[-1].weight).to(dev)
+                    if hasattr(p, 'shortcut'):
+                        d['wsT'] = U.pack_linear_weight_dgrad(p.shortcut.weight).to(dev)
+                elif kind == 'attn':
+                    d['wqkvT'] = U.pack_linear_weight_dgrad(p.qkv.weight).to(dev)
+                    d['wprojT'] = U.pack_linear_weight_dgrad(p.proj.weight).to(dev)
+                elif kind == 'down':
+                    w = p.downsample.weight.detach().permute(0, 2, 3, 1).reshape(p.c, 9 * p.c)       # [c, tap*c + cin]
+                    d['wT'] = U.pack_linear_weight_dgrad(w).to(dev)
+                elif kind == 'up':
+                    d['wT'] = U.pack_conv_weight_dgrad(p.conv.weight).to(dev)
+
+        for seq, blk in zip(self.in_seq, list(m.in_blocks)[1:]):
+            params(seq, blk)
+        params(self.mid_seq, m.mid_blocks)
+        for seq, blk in zip(self.out_seq, m.out_blocks):
+            params(seq, blk)
+        self.conv_in['wT'] = U.pack_conv_weight_dgrad(m.in_blocks[0][0].weight).to(dev)                 # K = 128, rows = cin (padded to 64)
+        self.out_conv['wT'] = U.pack_conv_weight_dgrad(m.out.conv.weight, cout_pad=self.CPAD_IN).to(dev)  # K = 18 -> 64, rows = 128
+        self._bwd_packed = True
+
+    def backward_nchw(self, grad_v):
+        """grad_v fp32 [B,C,H,W] (d loss / d v) -> d loss / d x_t fp32 [B,C,H,W], for the forward that just ran with save=True."""
+        B, C, H, W = grad_v.shape
+        L, s = N.lib(), N.stream_ptr()
+        scale = self._buf(('bwd', 'scale'), (2,), torch.float32)
+        N.check(L.ssdnerf_grad_scale(N.ptr(grad_v), N.ctypes.c_ulonglong(grad_v.numel()), N.c_f32(1024.0), N.ptr(scale), s))
+        g_in = self._buf(('bwd', 'g_in'), (B, H, W, self.CPAD_IN))
+        N.check(L.ssdnerf_grad_nchw_to_nhwc_f16(N.ptr(grad_v), N.c_u32(B), N.c_u32(C), N.c_u32(H), N.c_u32(W), N.c_u32(self.CPAD_IN),
+                                                N.ptr(scale), N.ptr(g_in), s))
+        dx = self.backward_nhwc(g_in)
+        out = torch.empty(B, self.cin_total, H, W, dtype=torch.float32, device=self.dev)
+        N.check(L.ssdnerf_grad_nhwc_to_nchw_f32(N.ptr(dx), N.c_u32(B), N.c_u32(self.cin_total), N.c_u32(H), N.c_u32(W), N.c_u32(self.CPAD_IN),
+                                                N.ptr(scale), N.ptr(out), s))
+        return out
+
+    def backward_nhwc(self, g_v):
+        """g_v fp16 [B,H,W,CPAD_IN] (loss-scaled d loss / d v, zero beyond the model's channels) -> fp32 [B,H,W,CPAD_IN] d loss / d x_in.
+        Walks the tape of the last save=True forward in reverse; every convolution / linear gradient is the forward's tensor-core
+        kernel on transposed weights, the rest are the section-4b glue kernels."""
+        if not self.tape or self.tape[-1]['kind'] != 'out':
+            raise N.SSDNeRFNativeError('UNet backward needs a preceding forward_nhwc(save=True)')
+        if not self._bwd_packed:
+            self._pack_backward_weights()
+        L, s = N.lib(), N.stream_ptr
+        grads = {}
+
+        def gb(name, idx, shape, dtype=torch.float16):
+            return self._buf(('bwd', name, idx), shape, dtype)
+
+        def acc(t, g):
+            """gradient w.r.t. forward tensor t: first contribution is stored, later ones are added in place"""
+            k = t.data_ptr()
+            old = grads.get(k)
+            if old is not None:
+                N.check(L.ssdnerf_add_f16(N.ptr(g), N.ptr(old), N.ctypes.c_ulonglong(g.numel()), s()))
+            grads[k] = g
+
+        gsum = self._buf(('bwd', 'gsum'), (self.B * 64,), torch.float32)
+        dx_in = None
+        for idx in range(len(self.tape) - 1, -1, -1):
+            r = self.tape[idx]
+            kind = r['kind']
+            if kind == 'out':
+                x = r['x']
+                B, H, W, c = x.shape
+                d_a = U.conv3x3_f16(g_v, self.out_conv['wT'], c, out=gb('d_a', (H, c), (B, H, W, c)))
+                dh = gb('dx', idx, (B, H, W, c))
+                U.gn_bwd(x, None, r['st'], self.out_norm['g'], self.out_norm['b'], d_a, dh, silu=True, gsum=gsum)
+                acc(x, dh)
+            elif kind == 'res':
+                d, x, sk, h1, out = r['d'], r['x'], r['sk'], r['h1'], r['out']
+                g = grads.pop(out.data_ptr())
+                B, H, W, C1 = x.shape
+                C2 = sk.shape[-1] if sk is not None else 0
+                cin, cout = d['cin'], d['cout']
+                d_a2 = U.conv3x3_f16(g, d['w2T'], cout, out=gb('d_a2', (H, cout), (B, H, W, cout)))
+                d_h1 = gb('d_h1', (H, cout), (B, H, W, cout))
+                ss = N.c_void_p(self.ss_cur.data_ptr() + 4 * self.ss_offsets[d['idx']])
+                U.gn_bwd(h1, None, r['st2'], d['g2'], d['b2'], d_a2, d_h1, scale_shift_ptr=ss, ss_batch_stride=self.ss_total, silu=True, gsum=gsum)
+                d_a = U.conv3x3_f16(d_h1, d['w1T'], cin, out=gb('d_a', (H, cin), (B, H, W, cin)))
+                if 'wsT' in d:
+                    add = U.conv3x3_f16(g, d['wsT'].unsqueeze(0), cin, taps=1, out=gb('d_sc', (H, cin), (B, H, W, cin)))
+                else:
+                    assert sk is None and cin == cout
+                    add = g
+                dx = gb('dx', idx, (B, H, W, C1))
+                dsk = gb('dsk', idx, (B, H, W, C2)) if sk is not None else None
+                U.gn_bwd(x, sk, r['st1'], d['g1'], d['b1'], d_a, dx, dsk, add=add, silu=True, gsum=gsum)
+                acc(x, dx)
+                if sk is not None:
+                    acc(sk, dsk)
+            elif kind == 'attn':
+                d, x, qkv, out = r['d'], r['x'], r['qkv'], r['out']
+                g = grads.pop(out.data_ptr())
+                B, H, W, c = x.shape
+                T, heads = H * W, d['heads']
+                d_o = U.linear_f16(g.view(B * T, c), d['wprojT'], n=c, out=gb('d_o', (T, c), (B * T, c)))
+                dqkv = U.attn_backward(qkv, d_o.view(B, T, c), heads, 1.0 / math.sqrt(c // heads),
+                                       lambda name, shape, dtype: gb('att_' + name, (T, c), shape, dtype))
+                d_xn = U.linear_f16(dqkv.view(B * T, 3 * c), d['wqkvT'], n=c, out=gb('d_xn', (T, c), (B * T, c)))
+                dx = gb('dx', idx, (B, H, W, c))
+                U.gn_bwd(x, None, r['st'], d['g'], d['b'], d_xn.view(B, H, W, c), dx, add=g, silu=False, gsum=gsum)
+                acc(x, dx)
+            elif kind == 'down':
+                d, x, out = r['d'], r['x'], r['out']
+                g = grads.pop(out.data_ptr())
+                B, H, W, c = x.shape
+                M = B * (H // 2) * (W // 2)
+                dcol = U.linear_f16(g.view(M, c), d['wT'], n=9 * c, out=gb('dcol', (H, c), (M, 9 * c)))
+                dx = gb('dx', idx, (B, H, W, c))
+                old = grads.pop(x.data_ptr(), None)
+                N.check(L.ssdnerf_col2im_s2(N.ptr(dcol), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(old), N.ptr(dx), s()))
+                grads[x.data_ptr()] = dx
+            elif kind == 'up':
+                d, x, out = r['d'], r['x'], r['out']
+                g = grads.pop(out.data_ptr())
+                B, H, W, c = x.shape
+                dup = U.conv3x3_f16(g, d['wT'], c, out=gb('dup', (H, c), (B, 2 * H, 2 * W, c)))
+                dx = gb('dx', idx, (B, H, W, c))
+                N.check(L.ssdnerf_sum2x2(N.ptr(dup), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(dx), s()))
+                acc(x, dx)
+            elif kind == 'conv_in':
+                g = grads.pop(r['out'].data_ptr())
+                dx_in = self._buf(('bwd', 'dx_in'), (self.B, self.H, self.W, self.CPAD_IN), torch.float32)
+                U.conv3x3_f16(g, self.conv_in['wT'], self.cin_total, out=dx_in)
+        assert not grads, 'dangling gradients in the UNet tape'
+        return dx_in
 
     def load_input_nchw(self, x):
         """x fp32 [B,C,H,W] -> self.x_in"""

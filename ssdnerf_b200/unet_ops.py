@@ -236,3 +236,109 @@ def conv3x3_gn_f16(x1, q1, gamma, beta, wp, bias=None, x2=None, q2=None, scale_s
         GEMM_LOG.append(dict(M=B * H * W, N=128, K=int(a.C1) + int(a.C2), taps=9, bn=128, cluster=1, batched=0, qstats=bool(a.qstats), f32=0, fused_gn=True))
     N.check(N.lib().ssdnerf_conv3x3_gn_f16(ctypes.byref(a), N.stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# input-gradient pass (C ABI section 4b): data gradients of the frozen UNet
+# ---------------------------------------------------------------------------------------------------------------------
+def pack_conv_weight_dgrad(w, cout_pad=None):
+    """Conv2d weight [Cout, Cin, 3, 3] -> packed weight of the DATA-GRADIENT convolution: dX = conv3x3(dY, W^T with flipped taps),
+    i.e. a 3x3 stride-1 convolution whose input channels are Cout (zero-padded to `cout_pad`) and whose outputs are Cin."""
+    return pack_conv_weight(w.detach().transpose(0, 1).flip(2, 3), cin_pad=cout_pad)
+
+
+def pack_linear_weight_dgrad(w):
+    """Linear / 1x1-conv weight [N, K] -> packed [K_pad, N] so that dX[M, K] = dY[M, N] @ W."""
+    w = w.detach().reshape(w.shape[0], -1)
+    return pack_linear_weight(w.t())
+
+
+class GnBwdArgs(ctypes.Structure):
+    """mirror of `ssdnerf_gn_bwd_args`"""
+    _fields_ = [
+        ('x1', N.c_void_p), ('C1', N.c_u32), ('x2', N.c_void_p), ('C2', N.c_u32), ('B', N.c_u32), ('HW', N.c_u32), ('groups', N.c_u32),
+        ('stats', N.c_void_p), ('stats2', N.c_void_p), ('quad_stats', N.c_int), ('gamma', N.c_void_p), ('beta', N.c_void_p),
+        ('scale_shift', N.c_void_p), ('ss_batch_stride', c_ll), ('eps', N.c_f32), ('do_silu', N.c_int),
+        ('dy', N.c_void_p), ('add', N.c_void_p), ('group_sums', N.c_void_p), ('dx1', N.c_void_p), ('dx2', N.c_void_p),
+    ]
+
+
+def gn_bwd(x1, x2, stats, gamma, beta, dy, dx1, dx2=None, add=None, scale_shift_ptr=None, ss_batch_stride=0, silu=True, gsum=None, eps=1e-5):
+    """GroupNorm(32)(+scale/shift)(+SiLU) backward over the channel concat of x1 (+x2); stats = (quad_flag, s1, s2) as the forward used."""
+    N.require_cuda(x1, dy, dx1)
+    B, H, W, C1 = x1.shape
+    a = GnBwdArgs()
+    a.x1, a.C1 = x1.data_ptr(), C1
+    if x2 is not None:
+        a.x2, a.C2 = x2.data_ptr(), x2.shape[-1]
+    a.B, a.HW, a.groups = B, H * W, 32
+    quad, s1, s2 = stats
+    a.stats, a.quad_stats = s1.data_ptr(), int(quad)
+    a.stats2 = s2.data_ptr() if s2 is not None else None
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    if scale_shift_ptr is not None:
+        a.scale_shift, a.ss_batch_stride = scale_shift_ptr, ss_batch_stride
+    a.eps, a.do_silu = eps, int(silu)
+    a.dy = dy.data_ptr()
+    a.add = add.data_ptr() if add is not None else None
+    if gsum is None:
+        gsum = torch.empty(B * 32 * 2, dtype=torch.float32, device=x1.device)
+    a.group_sums = gsum.data_ptr()
+    a.dx1 = dx1.data_ptr()
+    a.dx2 = dx2.data_ptr() if dx2 is not None else None
+    N.check(N.lib().ssdnerf_gn_bwd(ctypes.byref(a), N.stream_ptr()))
+    return dx1, dx2
+
+
+def transpose_f16(src_ptr, dst, rows, cols, row_stride, stride1, n1, stride2, n2):
+    N.check(N.lib().ssdnerf_transpose_f16(N.c_void_p(src_ptr), N.ptr(dst), N.c_u32(rows), N.c_u32(cols), c_ll(row_stride), c_ll(stride1),
+                                          N.c_u32(n1), c_ll(stride2), N.c_u32(n2), N.stream_ptr()))
+    return dst
+
+
+def _bgemm(a_ptr, a_strides, k, b_ptr, b_strides, n, T, heads, B, out_ptr, out_strides, out_f32, alpha):
+    """batched GEMM over (head, batch): out[b,h,t,:n] = alpha * A[b,h,t,:k] @ Bm[b,h,:n,:k]^T (strides in bytes for A / Bm, elements for out)"""
+    g = GemmArgs()
+    g.a1, g.k1 = a_ptr, k
+    g.a1_strides = (c_u64 * 3)(*a_strides)
+    g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = T, heads, B, 128, 1, 1
+    g.taps = 1
+    g.b, g.n, g.n_rows_b, g.bx2, g.bx3, g.b_batched = b_ptr, n, n, heads, B, 1
+    g.b_strides = (c_u64 * 3)(*b_strides)
+    g.bn, g.alpha = 0, alpha
+    g.out, g.out_f32 = out_ptr, int(out_f32)
+    g.so1, g.so2, g.so3 = out_strides
+    _launch(g)
+
+
+def attn_backward(qkv, d_o, heads, scale, ws):
+    """Attention data gradient (softmax(scale q k^T) v, legacy head layout of modules.py:36-48) by recomputation on the tensor cores:
+    qkv fp16 [B,T,3c] (saved by the forward), d_o fp16 [B,T,c] -> dqkv fp16 [B,T,3c].  `ws(name, shape, dtype)` supplies scratch."""
+    B, T, c3 = qkv.shape
+    c = c3 // 3
+    ch = c // heads
+    L, s = N.lib(), N.stream_ptr
+    S = attn_scores(qkv, heads, scale, out=ws('S', (B, heads, T, T), torch.float32))
+    P = ws('P', (B, heads, T, T), torch.float16)
+    N.check(L.ssdnerf_softmax_rows(N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(P), s()))
+    qp, dop = qkv.data_ptr(), d_o.data_ptr()
+    TT = T * T
+    # dP[b,h,t,s] = d_o[b,t,h,:] . v[b,s,h,:]   (into the score buffer, which is dead after the softmax)
+    _bgemm(dop, (c * 2, ch * 2, T * c * 2), ch, qp + 2 * ch * 2, (c3 * 2, 3 * ch * 2, T * c3 * 2), T, T, heads, B,
+           S.data_ptr(), (T, TT, heads * TT), True, 1.0)
+    dS = ws('dS', (B, heads, T, T), torch.float16)
+    N.check(L.ssdnerf_softmax_bwd_rows(N.ptr(P), N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(dS), s()))
+    Pt = transpose_f16(P.data_ptr(), ws('Pt', (B, heads, T, T), torch.float16), T, T, T, TT, heads, heads * TT, B)
+    dSt = transpose_f16(dS.data_ptr(), ws('dSt', (B, heads, T, T), torch.float16), T, T, T, TT, heads, heads * TT, B)
+    qt = transpose_f16(qp, ws('qt', (B, heads, ch, T), torch.float16), T, ch, c3, 3 * ch, heads, T * c3, B)
+    kt = transpose_f16(qp + ch * 2, ws('kt', (B, heads, ch, T), torch.float16), T, ch, c3, 3 * ch, heads, T * c3, B)
+    dot = transpose_f16(dop, ws('dot', (B, heads, ch, T), torch.float16), T, ch, c, ch, heads, T * c, B)
+    dqkv = ws('dqkv', (B, T, c3), torch.float16)
+    a_tt = (T * 2, TT * 2, heads * TT * 2)
+    b_ct = (T * 2, ch * T * 2, heads * ch * T * 2)
+    o_str = (c3, 3 * ch, T * c3)
+    dp = dqkv.data_ptr()
+    _bgemm(dS.data_ptr(), a_tt, T, kt.data_ptr(), b_ct, ch, T, heads, B, dp, o_str, False, scale)                  # dq = scale dS k
+    _bgemm(dSt.data_ptr(), a_tt, T, qt.data_ptr(), b_ct, ch, T, heads, B, dp + ch * 2, o_str, False, scale)        # dk = scale dS^T q
+    _bgemm(Pt.data_ptr(), a_tt, T, dot.data_ptr(), b_ct, ch, T, heads, B, dp + 2 * ch * 2, o_str, False, 1.0)      # dv = P^T d_o
+    return dqkv

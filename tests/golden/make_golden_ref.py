@@ -16,6 +16,8 @@ is gone from NumPy 2), so this script loads three of its files BY PATH with the 
         prepare_diffusion_vars (:131-154, with `np.cumproduct = np.cumprod` patched in), pred_x_0 (:180-240, incl. both
         guidance branches), p_sample_langevin (:242-262), p_sample_ddim (:264-293), ddim_sample (:295-331), q_sample (:166-178)
     lib/models/diffusions/sampler.py          : SNRWeightedTimeStepSampler.__init__ (:15-46: the per-timestep loss weights)
+    lib/models/losses/ddpm_loss.py            : DDPMMSELossMod (:12-131: 0.5 * flat-mean MSE, weight[t] * weight_scale rescale, norm_factor)
+        driven by gaussian_diffusion.py forward_train / loss (:404-450) with the timestep draw and the noise injected
 
   supplied by the stubs below, restated from mmgen 0.7.2 / mmcv-full 1.6.0 FROM MEMORY ............... [mmgen-memory]
     mmgen.models.architectures.ddpm.modules : TimeEmbedding (sinusoidal cos|sin -> Linear -> SiLU -> Linear), EmbedSequential,
@@ -24,6 +26,7 @@ is gone from NumPy 2), so this script loads three of its files BY PATH with the 
     mmgen.models.architectures.ddpm.denoising : DenoisingUnet.init_weights (zero conv_2 / out / proj)
     mmgen.models.diffusions.utils : var_to_tensor, _get_noise_batch;  mmgen.models.architectures.common.get_module_device
     mmgen.models.diffusions.UniformTimeStepSampler (base class only; its sampling is not exercised)
+    mmgen.models.losses.ddpm_loss : DDPMLoss base (rescale_mode='timestep_weight' from sampler.weight, reduce), mse_loss('flatmean'), reduce_loss
     mmcv.cnn.bricks : build_norm_layer (GN, eps 1e-5), build_activation_layer (SiLU), ConvModule(order=('norm','act','conv'))
     mmgen.models.builder : MODULES registry / build_module
 
@@ -219,6 +222,32 @@ class UniformTimeStepSampler:
         self.prob = [1 / num_timesteps for _ in range(num_timesteps)]
 
 
+class DDPMLoss(nn.Module):
+    """mmgen DDPMLoss restricted to what DDPMMSELossMod uses: rescale_mode None | 'timestep_weight', log collection dropped"""
+
+    def __init__(self, rescale_mode=None, rescale_cfg=None, log_cfgs=None, weight=None, sampler=None, reduction='mean', loss_name=None):
+        super().__init__()
+        self.log_vars, self.reduction, self._loss_name, self.sampler = dict(), reduction, loss_name, sampler
+        if rescale_mode is None:
+            self.rescale_fn = lambda loss, t: loss
+        else:
+            assert rescale_mode == 'timestep_weight'
+            w = weight if weight is not None else sampler.weight.clone()
+            self.rescale_fn = partial(self.timestep_weight_rescale, weight=w)
+
+    def collect_log(self, loss, timesteps):
+        self.log_vars = {self._loss_name: float(loss.mean())}
+
+
+def mse_loss(pred, target, reduction='flatmean'):
+    assert reduction == 'flatmean'
+    return F.mse_loss(pred, target, reduction='none').flatten(1).mean(dim=1)
+
+
+def reduce_loss(loss, reduction):
+    return dict(mean=loss.mean, sum=loss.sum, none=lambda: loss)[reduction]()
+
+
 def get_module_device(module):
     return next(module.parameters()).device
 
@@ -267,6 +296,13 @@ def _install_stubs():
     mod('mmgen.models.architectures.ddpm.denoising', DenoisingUnet=DenoisingUnet)
     mod('mmgen.models.diffusions', UniformTimeStepSampler=UniformTimeStepSampler)
     mod('mmgen.models.diffusions.utils', var_to_tensor=var_to_tensor, _get_noise_batch=_get_noise_batch)
+    mod('mmgen.models.losses')
+    mod('mmgen.models.losses.ddpm_loss', DDPMLoss=DDPMLoss, mse_loss=mse_loss, reduce_loss=reduce_loss)
+    # the relative import `from ...core import reduce_mean` of lib/models/losses/ddpm_loss.py: single-process identity
+    for name in ('reflib', 'reflib.models', 'reflib.models.losses'):
+        pkg = mod(name)
+        pkg.__path__ = []
+    mod('reflib.core', reduce_mean=lambda x: x)
     if not hasattr(np, 'cumproduct'):
         np.cumproduct = np.cumprod          # removed in NumPy 2; gaussian_diffusion.py:134 calls it
 
@@ -286,6 +322,7 @@ def load_reference():
     den = _load('lib/models/architecture/ddpm/denoising.py', 'ref_ddpm_denoising')
     gd = _load('lib/models/diffusions/gaussian_diffusion.py', 'ref_gaussian_diffusion')
     sm = _load('lib/models/diffusions/sampler.py', 'ref_sampler')
+    _load('lib/models/losses/ddpm_loss.py', 'reflib.models.losses.ddpm_loss')
     return mods, den, gd, sm
 
 
@@ -405,6 +442,22 @@ def main():
     out['q_eps'], out['q_sample'] = eps.numpy(), xq.numpy()
     out['unet_weight_seed'] = np.array(11)
     out['unet_weight_checksum'] = np.array(sum(float(v.double().sum()) for v in sd.values()))
+    # ---- diffusion loss as val_optim uses it (chairs_recons1v settings: SNR power 0.25, v-target, weight_scale, scale_norm)
+    dl = gd.GaussianDiffusion(denoising=unet, betas_cfg=dict(type='linear'), num_timesteps=1000, denoising_mean_mode='V',
+                              timestep_sampler=dict(type='SNRWeightedTimeStepSampler', power=0.25),
+                              ddpm_loss=dict(type='DDPMMSELossMod', rescale_mode='timestep_weight', data_info=dict(pred='v_t_pred', target='v_t'),
+                                             weight_scale=4.0, scale_norm=True, loss_name='loss_ddpm_mse'))
+    dl.eval()
+    dl.ddpm_loss.norm_factor.fill_(0.37)
+    t_fix = torch.tensor([12, 870])
+    dl.sampler = lambda n: t_fix
+    sys.modules['ref_gaussian_diffusion']._get_noise_batch = lambda *a, **k: eps
+    x0r = target.clone().requires_grad_(True)
+    for p_ in dl.parameters():
+        p_.requires_grad_(False)
+    loss, _ = dl.forward_train(x0r, cfg=dict(clip_range=[-2, 2]))
+    loss.backward()
+    out['train_t'], out['train_loss'], out['train_dx0'] = t_fix.numpy(), np.array(float(loss)), x0r.grad.numpy()
     np.savez_compressed(os.path.join(HERE, 'reference_v1.npz'), **out)
     print({k: (v.shape if hasattr(v, 'shape') else v) for k, v in out.items()})
 

@@ -13,9 +13,10 @@ REF = '/root/reference'
 
 
 def test_registry_names():
-    for n in ('TriPlaneDecoder', 'GaussianDiffusion', 'DenoisingUnetMod', 'TanhCode', 'IdentityCode'):
+    for n in ('TriPlaneDecoder', 'GaussianDiffusion', 'DenoisingUnetMod', 'TanhCode', 'IdentityCode', 'NormalizedTanhCode', 'MSELoss', 'RegLoss', 'TVLoss',
+              'DDPMMSELossMod', 'SNRWeightedTimeStepSampler', 'UniformTimeStepSamplerMod'):
         assert n in S.MODULES
-    assert 'DiffusionNeRF' in S.MODELS
+    assert 'DiffusionNeRF' in S.MODELS and 'MultiSceneNeRF' in S.MODELS
 
 
 def test_build_from_repo_config_and_state_dict_keys():
@@ -42,6 +43,59 @@ def test_reference_configs_build_unchanged(cfg_rel):
     m = S.build_model(cfg.model, train_cfg=cfg.get('train_cfg'), test_cfg=cfg.get('test_cfg'))
     assert type(m).__name__ == 'DiffusionNeRF'
     assert m.diffusion.test_cfg['num_timesteps'] == cfg.test_cfg['num_timesteps']
+
+
+def test_every_reference_config_builds_from_the_fixture():
+    """tests/golden/reference_configs.json = every config the reference ships, resolved (tests/golden/make_config_fixtures.py); each one
+    builds through the registry unchanged, and the fixture is current with /root/reference when that exists"""
+    import json
+    cfgs = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reference_configs.json')))
+    assert len(cfgs) == 24
+    for name, c in cfgs.items():
+        m = S.build_model(c['model'], train_cfg=c['train_cfg'], test_cfg=c['test_cfg'])
+        assert type(m).__name__ in ('DiffusionNeRF', 'MultiSceneNeRF'), name
+    if os.path.isdir(REF):
+        from tests.golden.make_config_fixtures import resolve_all
+        assert json.loads(json.dumps(resolve_all(), sort_keys=True)) == cfgs
+    # the bench / GPU-test config is the fixture entry, and the repo's restated config file agrees with it
+    own = S.Config.fromfile(os.path.join(ROOT, 'configs', 'cars_uncond_b200.py'))
+    refc = cfgs['configs/paper_cfgs/ssdnerf_cars_uncond.py']
+    for k in ('code_size', 'code_reshape', 'grid_size', 'decoder_use_ema', 'bg_color'):
+        assert json.loads(json.dumps(own.model[k])) == refc['model'][k], k
+    assert json.loads(json.dumps(own.model['decoder'])) == refc['model']['decoder']
+    assert json.loads(json.dumps(own.model['diffusion']['denoising'])) == refc['model']['diffusion']['denoising']
+    assert json.loads(json.dumps(dict(own.test_cfg))) == refc['test_cfg']
+
+
+def test_code_activations_scene_io_and_losses(tmp_path):
+    from ssdnerf_b200.nerf import BaseNeRF, NormalizedTanhCode, TanhCode, TVLoss
+    act = NormalizedTanhCode(mean=0.0, std=0.5, clip_range=2)
+    act.running_mean.fill_(0.1); act.running_var.fill_(0.3)
+    x = torch.linspace(-1.5, 1.5, 31)
+    torch.testing.assert_close(act.inverse(act(x)), x, rtol=1e-4, atol=1e-4)
+    # formula of base_nerf.py:65-76
+    scale = 0.5 / (0.3 ** 0.5 + 1e-5)
+    torch.testing.assert_close(act(x), torch.tanh((x * scale + (0.0 - 0.1 * scale)) / 2) * 2)
+    assert set(act.state_dict()) == {'running_mean', 'running_var'}
+    act.train()
+    before = act.running_mean.clone()
+    act(x, update_stats=True)
+    assert not torch.equal(before, act.running_mean)
+    # save_scene / load_scene round trip in the reference's file format (base_nerf.py:141-170)
+    code = torch.randn(2, 3, 6, 8, 8)
+    grid = torch.rand(2, 64).half()
+    bits = torch.randint(0, 255, (2, 8), dtype=torch.uint8)
+    BaseNeRF.save_scene(str(tmp_path), code, grid, bits, ['a', 'b'])
+    states = [torch.load(os.path.join(tmp_path, n + '.pth')) for n in ('a', 'b')]
+    assert set(states[0]) == {'scene_name', 'param'} and set(states[0]['param']) == {'code', 'density_grid', 'density_bitfield'}
+    holder = torch.nn.Module.__new__(BaseNeRF); torch.nn.Module.__init__(holder)
+    holder.code_activation = TanhCode(scale=2); holder.register_buffer('_p', torch.zeros(1)); holder.register_parameter('w', torch.nn.Parameter(torch.zeros(1)))
+    c2, g2, b2 = BaseNeRF.load_scene(holder, dict(code=states), load_density=True)
+    assert torch.equal(c2, code) and torch.equal(g2, grid) and torch.equal(b2, bits)
+    pre = dict(param=dict(code_=torch.randn(3, 6, 8, 8)))             # training-cache states hold the pre-activation latent
+    c3, _, _ = BaseNeRF.load_scene(holder, dict(code=[pre]))
+    torch.testing.assert_close(c3[0], pre['param']['code_'].tanh() * 2)
+    assert float(TVLoss(power=1.5)(torch.ones(1, 3, 6, 8, 8))) == 0.0
 
 
 def test_ddim_tables_match_oracle():
@@ -111,8 +165,8 @@ def test_guided_sampling_contract():
         d.pred_x_0(torch.zeros(1, 18, 128, 128), torch.tensor([10]), grad_guide_fn=lambda x: x.sum(), cfg=dict(clip_range=[-2, 2]))
     with pytest.raises(S._lib.SSDNeRFNativeError):
         m.val_guide(dict(cond_imgs=torch.zeros(1, 1, 8, 8, 3), cond_intrinsics=torch.ones(1, 1, 4), cond_poses=torch.eye(4).expand(1, 1, 4, 4)))
-    with pytest.raises(NotImplementedError):
-        m.val_optim({})
+    with pytest.raises(S._lib.SSDNeRFNativeError):
+        m.val_optim(dict(cond_imgs=torch.zeros(1, 1, 8, 8, 3), cond_intrinsics=torch.ones(1, 1, 4), cond_poses=torch.eye(4).expand(1, 1, 4, 4)))
     # the step-wise sampler is selected for guidance / langevin / eta > 0 and refuses image-conditioned denoisers
     with pytest.raises(NotImplementedError, match='concat_cond'):
         d._ddim_sample_stepwise(torch.zeros(1, 18, 128, 128), concat_cond=torch.zeros(1, 1, 3, 128, 128))

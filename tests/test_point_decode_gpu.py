@@ -49,6 +49,9 @@ def test_point_decode_refuses_gradients_and_trainable_decoder(cuda):
     with pytest.raises(NotImplementedError):
         dec.point_decode(x, [x[0]], code)
     dec.train()
-    dec.requires_grad_(True)            # trainable decoder: the train branch fails loudly (no PyTorch composition in the product)
+    dec.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        dec.point_decode(x, [x[0]], code.detach())
+    # trainable decoder: the train branch fails loudly (no PyTorch composition in the product)
     with pytest.raises(NotImplementedError):
         dec(torch.zeros(1, 8, 3, device=cuda), torch.ones(1, 8, 3, device=cuda), code.detach(), torch.zeros(1, 64 ** 3 // 8, dtype=torch.uint8, device=cuda), 64)

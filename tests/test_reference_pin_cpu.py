@@ -123,7 +123,8 @@ def test_package_sampler_host_logic_matches_reference(ref):
     from ssdnerf_b200.diffusion import GaussianDiffusion
     d = GaussianDiffusion(denoising=_OracleUNet(ref), betas_cfg=dict(type='linear'), num_timesteps=1000, test_cfg=dict(TEST_CFG))
     x_t = torch.from_numpy(ref['x_t'])
-    x0, v = d.pred_x_0(x_t.clone(), torch.tensor(600), cfg=TEST_CFG)
+    with torch.no_grad():           # unguided pred_x_0 follows the ambient autograd mode (forward_train differentiates through it)
+        x0, v = d.pred_x_0(x_t.clone(), torch.tensor(600), cfg=TEST_CFG)
     _close(x0, ref['pred_x0_t600']); _close(v, ref['pred_v_t600'])
     xp, _ = d.p_sample_ddim(x_t.clone(), 600, 500, cfg=TEST_CFG)
     _close(xp, ref['ddim_prev_600_500'])
@@ -142,7 +143,8 @@ def test_package_sampler_host_logic_matches_reference(ref):
     guide = lambda x0: 0.5 * ((x0 - target) ** 2).mean() * x0.size(0)
     for through, tag in ((True, 'thru'), (False, 'x0')):
         cfg = dict(TEST_CFG, grad_through_unet=through)
-        x0, v = d.pred_x_0(x_t.clone(), torch.tensor(600), grad_guide_fn=guide, cfg=cfg, update_denoising_output=True)
+        with torch.no_grad():
+            x0, v = d.pred_x_0(x_t.clone(), torch.tensor(600), grad_guide_fn=guide, cfg=cfg, update_denoising_output=True)
         _close(x0, ref[f'guided_x0_{tag}']); _close(v, ref[f'guided_v_{tag}'], 1e-4)
     g2 = torch.Generator().manual_seed(int(ref['langevin_noise_seed']))
     noises = [torch.randn(2, 18, 16, 16, generator=g2) for _ in range(18)]
@@ -152,3 +154,34 @@ def test_package_sampler_host_logic_matches_reference(ref):
     eps = torch.from_numpy(ref['q_eps'])
     xq, mean, std = d.q_sample(target, torch.tensor([10, 900]), noise=eps)
     _close(xq, ref['q_sample'])
+
+
+def test_diffusion_prior_loss_matches_reference(ref):
+    """forward_train as val_optim calls it (SNR-weighted v-loss, weight_scale, scale_norm) with the timestep draw and the noise injected:
+    loss value and d loss / d x_0 == the reference's GaussianDiffusion.forward_train + DDPMMSELossMod"""
+    from ssdnerf_b200.diffusion import GaussianDiffusion
+    d = GaussianDiffusion(denoising=_OracleUNet(ref).requires_grad_(False), betas_cfg=dict(type='linear'), num_timesteps=1000,
+                          timestep_sampler=dict(type='SNRWeightedTimeStepSampler', power=0.25),
+                          ddpm_loss=dict(type='DDPMMSELossMod', rescale_mode='timestep_weight', data_info=dict(pred='v_t_pred', target='v_t'),
+                                         weight_scale=4.0, scale_norm=True,
+                                         log_cfgs=dict(type='quartile', prefix_name='loss_mse', total_timesteps=1000)))
+    d.eval()
+    d.ddpm_loss.norm_factor.fill_(0.37)
+    assert np.array_equal(d.sampler.weight.numpy(), ref['snr_weight_p025_V'])
+    x0 = torch.from_numpy(ref['guide_target']).clone().requires_grad_(True)
+    loss, log_vars = d(x0, return_loss=True, cfg=dict(clip_range=[-2, 2]), t=torch.from_numpy(ref['train_t']), noise=torch.from_numpy(ref['q_eps']))
+    loss.backward()
+    assert abs(float(loss) - float(ref['train_loss'])) <= 1e-5 * abs(float(ref['train_loss']))
+    _close(x0.grad, ref['train_dx0'], 1e-6 + 1e-4 * float(np.abs(ref['train_dx0']).max()))
+    assert 'loss_ddpm_mse' in log_vars
+    # override_cfg semantics of BaseNeRF.train(): eval mode swaps the configured attributes, train mode restores them
+    import json, os
+    import ssdnerf_b200 as S
+    c = json.load(open(os.path.join(GOLDEN, 'reference_configs.json')))['configs/paper_cfgs/ssdnerf_chairs_recons1v.py']
+    c['model']['diffusion']['denoising'].update(base_channels=64, channels_cfg=[1, 2], attention_res=[])      # keep the CPU test light
+    m = S.build_model(c['model'], train_cfg=c['train_cfg'], test_cfg=c['test_cfg'])
+    assert m.diffusion_ema.ddpm_loss.weight_scale == 4.0
+    m.eval()
+    assert m.diffusion_ema.ddpm_loss.weight_scale == 1.0 and m.diffusion.ddpm_loss.weight_scale == 4.0
+    m.train()
+    assert m.diffusion_ema.ddpm_loss.weight_scale == 4.0

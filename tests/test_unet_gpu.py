@@ -1,8 +1,13 @@
-"""UNet / DDIM on the GPU (tcgen05 GEMMs, fp16 activations, fp32 accumulation) vs the fp32 PyTorch-CPU oracle.
+"""UNet / DDIM on the GPU (tcgen05 GEMMs, fp16 operands + activation storage, fp32 accumulation) vs the fp32 oracle
+(oracle/unet_port.py, pinned to the reference's own code by tests/test_reference_pin_cpu.py).
 
-Tolerance: BASELINE.json north_star asks for denoised triplanes within 1e-3 relative at fp16; the oracle here is fp32 (the
-reference's GPU path runs TF32 convs), so we bound the relative L2 error of one UNet evaluation
-by 3e-3 and of a short DDIM chain by 1e-2, and report the measured values."""
+Tolerance.  BASELINE.json north_star: "denoised triplanes within 1e-3 relative fp16 tolerance".  An fp32 oracle cannot be matched to
+1e-3 by ANY single-pass 10/11-bit-mantissa tensor-core path: scripts/precision_probe.py (profiles/r02_precision_probe.txt) injects
+the roundings one at a time into the fp32 oracle at full size -- fp16 GEMM operands alone 1.28e-3, the reference's own default
+(cuDNN TF32 convolutions) 1.28e-3, fp16 storage of h1 +0.62e-3, of the residual stream +0.67e-3 (RSS total
+1.54e-3 = what the GPU measures).  The bars below are therefore stated against that floor: one evaluation <= 2.0e-3 relative L2
+(measured 1.4-1.5e-3), i.e. within 1.2x of the reference's own TF32 deviation from fp32; the full-size 50-step chain is bounded
+at the value measured on the B200 with 30 % margin and reported."""
 import math
 
 import numpy as np
@@ -97,7 +102,7 @@ def test_small_unet_forward(cuda, B):
     out = m(x.to(cuda), t.to(cuda)).cpu()
     err = _rel_l2(out, ref)
     print('small unet rel l2', err)
-    assert out.shape == ref.shape and err < 3e-3
+    assert out.shape == ref.shape and err < 2e-3
 
 
 def test_ddim_graph_equals_eager_and_tracks_oracle(cuda):
@@ -138,7 +143,36 @@ def test_full_unet_one_step_vs_oracle(cuda):
     ref = up.unet_forward(sd, spec, x, t)
     err = _rel_l2(out, ref)
     print('full unet rel l2', err)
-    assert err < 3e-3
+    assert err < 2e-3
+
+
+def test_full_size_50_step_ddim_vs_fp32_oracle(cuda):
+    """ssdnerf_cars_uncond UNet, the whole 50-step DDIM chain at B=1: captured-graph loop vs the fp32 oracle chain.  The oracle runs
+    on the same GPU in strict fp32 (TF32 off): 50 x 218 GFLOP would take minutes on host cores."""
+    from ssdnerf_b200.diffusion import GaussianDiffusion
+    full = dict(image_size=128, in_channels=18, base_channels=128, channels_cfg=[1, 2, 2, 4, 4], resblocks_per_downsample=2,
+                num_heads=4, attention_res=[32, 16, 8], use_scale_shift_norm=True)
+    spec = up.unet_spec()
+    sd = up.random_state_dict(spec, seed=7, std=0.02)
+    m = _build(full, sd, cuda)
+    diff = GaussianDiffusion(m, betas_cfg=dict(type='linear'), num_timesteps=1000, test_cfg=dict(num_timesteps=50, clip_range=[-2, 2])).to(cuda)
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(1, 18, 128, 128, generator=g)
+    out = diff(noise.to(cuda), return_loss=False).cpu()
+    up.fp32_reference_mode()
+    sdg = up.state_dict_to(sd, cuda)
+    dv = up.diffusion_vars(up.linear_betas())
+    with torch.no_grad():
+        # cross-check the GPU-resident oracle against the CPU oracle on one evaluation (same arithmetic, different library kernels)
+        x1 = torch.randn(1, 18, 128, 128, generator=g)
+        t1 = torch.tensor([400])
+        a = up.unet_forward(sdg, spec, x1.to(cuda), t1.to(cuda)).cpu()
+        b = up.unet_forward(sd, spec, x1, t1)
+        assert _rel_l2(a, b) < 2e-5, _rel_l2(a, b)
+        ref = up.ddim_sample(lambda x, t: up.unet_forward(sdg, spec, x, t.to(x.device)), noise.to(cuda), dv, num_timesteps=50, clip_range=(-2, 2)).cpu()
+    err = _rel_l2(out, ref)
+    print('full-size 50-step DDIM rel l2', err, 'max abs', float((out - ref).abs().max()), 'ref rms', float(ref.pow(2).mean().sqrt()))
+    assert err < 1e-2
 
 
 def test_fused_quad_stats_match_tensor(cuda):
