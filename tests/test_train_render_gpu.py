@@ -178,16 +178,18 @@ def test_loss_fused_vs_oracle_and_module_composition(cuda):
     assert _rel_l2(res[True][1], res[False][1]) < 1e-4
 
 
-def test_guided_ddim_matches_oracle(cuda):
-    """val_guide (grad_through_unet=False) on a small UNet: render-loss guidance + langevin steps vs the oracle chain.
-    The UNet runs fp16 tensor-core GEMMs and guidance feeds its output back, so the comparison is relative-L2 on the code."""
+@pytest.mark.parametrize('through_unet', [False, True])
+def test_guided_ddim_matches_oracle(cuda, through_unet):
+    """val_guide on a small UNet: render-loss guidance (gradient w.r.t. x_0, or w.r.t. x_t THROUGH the denoiser -- the reference
+    default, gaussian_diffusion.py:213-216 -- on the native input-gradient pass) + langevin steps vs the oracle chain.  The UNet runs
+    fp16 tensor-core GEMMs and guidance feeds its output back, so the comparison is relative-L2 on the code."""
     params = rp.make_decoder_params('P', 11)
     params['density_net.0.bias'] = params['density_net.0.bias'] + 1.5
     spec = up.unet_spec(image_size=128, in_channels=18, base_channels=64, channels_cfg=(1, 2), resblocks_per_downsample=1,
                         attention_res=(), num_heads=2)
     sd = up.random_state_dict(spec, seed=4, std=0.03)
     test_cfg = dict(num_timesteps=4, clip_range=[-2, 2], density_thresh=0.1, n_inverse_rays=2 ** 10, loss_coef=0.1 / (32 * 32),
-                    guidance_gain=0.4 * (2 ** 10), snr_weight_power=0.25, grad_through_unet=False, langevin_steps=1, langevin_delta=0.4,
+                    guidance_gain=0.4 * (2 ** 10), snr_weight_power=0.25, grad_through_unet=through_unet, langevin_steps=1, langevin_delta=0.4,
                     langevin_t_range=[0, 600], dt_gamma_scale=0.5)
     model = _model(cuda, params, test_cfg, sd, spec)
     B, res = 1, 32
@@ -197,46 +199,49 @@ def test_guided_ddim_matches_oracle(cuda):
     f = 131.25 * res / 128
     intr = torch.tensor([f, f, res / 2, res / 2]).expand(B, 1, 4).contiguous()
     cond_imgs = torch.rand(B, 1, res, res, 3, generator=g)
-    with pytest.raises(NotImplementedError):                                  # the reference default needs the UNet backward (f1)
-        model.test_cfg['grad_through_unet'] = True
-        model.diffusion.test_cfg['grad_through_unet'] = True
-        model.val_guide(dict(cond_imgs=cond_imgs.to(cuda), cond_intrinsics=intr.to(cuda), cond_poses=poses.to(cuda), noise=noise.to(cuda)))
-    model.test_cfg['grad_through_unet'] = False
-    model.diffusion.test_cfg['grad_through_unet'] = False
 
     # deterministic replicas of the random draws: langevin noise, perturb offsets and the occupancy jitter are injected
     lang = [torch.randn(B, 18, 128, 128, generator=g) for _ in range(8)]
     pert = [torch.rand(B, res * res, generator=g) for _ in range(16)]
     jit = [torch.rand(64 ** 3, 3, generator=g) for _ in range(16)]
-    it = dict(l=iter(lang), p=iter(pert), j=iter(jit))
-    orig_loss, orig_ues, orig_lang = model.loss, model.update_extra_state, model.diffusion.p_sample_langevin
+    it = dict(p=iter(pert), j=iter(jit))
+    orig_loss, orig_ues = model.loss, model.update_extra_state
     model.loss = lambda *a, **k: orig_loss(*a, **dict(k, perturb=next(it['p']).to(cuda)))
     model.update_extra_state = lambda *a, **k: orig_ues(*a, **dict(k, jitter=next(it['j']).to(cuda)))
-    model.diffusion.p_sample_langevin = lambda x, t, **k: orig_lang(x, t, **dict(k, noise=next(it['l']).to(cuda)))
-    code_gpu, grid_gpu, bits_gpu = model.val_guide(dict(cond_imgs=cond_imgs.to(cuda), cond_intrinsics=intr.to(cuda), cond_poses=poses.to(cuda),
-                                                        noise=noise.to(cuda)))
+    data = dict(cond_imgs=cond_imgs.to(cuda), cond_intrinsics=intr.to(cuda), cond_poses=poses.to(cuda), noise=noise.to(cuda))
+    code_gpu, grid_gpu, bits_gpu = model.val_guide(data, langevin_noises=iter([n.to(cuda) for n in lang]))
     # oracle chain
     ro, rd = rp.get_cam_rays(poses, intr, res, res)
     dtg = (0.5 / intr[..., :2].mean(dim=(-2, -1))).numpy()
     grid = torch.zeros(B, 64 ** 3)
     it2 = dict(p=iter(pert), j=iter(jit))
 
-    def grad_fn(x0):
-        code_pred = x0.reshape(B, 3, 6, 128, 128)
-        bits, _ = rp.update_extra_state(params, code_pred, grid, next(it2['j']), density_thresh=0.1, decay=0.9)
-        _, grad, _ = tp.render_loss_grad(params, code_pred, ro.reshape(B, -1, 3).numpy(), rd.reshape(B, -1, 3).numpy(),
-                                         cond_imgs.reshape(B, -1, 3).numpy(), bits, noises=next(it2['p']).numpy(), dt_gamma=dtg, bg_color=1.0,
-                                         pixel_weight=20.0, loss_coef=test_cfg['loss_coef'], scale_num_ray=res * res, reg_weight=3e-3)
-        return (grad * B).reshape(x0.shape).float()
+    class _RenderLoss(torch.autograd.Function):
+        """oracle render loss as an autograd node (value + analytic gradient from oracle/train_port.py)"""
+
+        @staticmethod
+        def forward(ctx, x0):
+            code_pred = x0.detach().reshape(B, 3, 6, 128, 128)
+            bits, _ = rp.update_extra_state(params, code_pred, grid, next(it2['j']), density_thresh=0.1, decay=0.9)
+            with torch.enable_grad():          # autograd.Function.forward runs with grad mode off; the oracle differentiates internally
+                loss, grad, _ = tp.render_loss_grad(params, code_pred, ro.reshape(B, -1, 3).numpy(), rd.reshape(B, -1, 3).numpy(),
+                                                    cond_imgs.reshape(B, -1, 3).numpy(), bits, noises=next(it2['p']).numpy(), dt_gamma=dtg, bg_color=1.0,
+                                                    pixel_weight=20.0, loss_coef=test_cfg['loss_coef'], scale_num_ray=res * res, reg_weight=3e-3)
+            ctx.save_for_backward((grad * B).reshape(x0.shape).float())
+            return torch.as_tensor(float(loss) * B)
+
+        @staticmethod
+        def backward(ctx, g_out):
+            return ctx.saved_tensors[0] * g_out
 
     dv = up.diffusion_vars(up.linear_betas())
-    ref = tp.guided_ddim_sample(lambda x, t: up.unet_forward(sd, spec, x, t), noise.reshape(B, 18, 128, 128), dv, grad_fn, num_timesteps=4,
-                                guidance_gain=test_cfg['guidance_gain'], snr_weight_power=0.25, langevin_steps=1, langevin_delta=0.4,
-                                langevin_t_range=(0, 600), langevin_noises=lang)
+    ref = up.ddim_sample_guided(lambda x, t: up.unet_forward(sd, spec, x, t), noise.reshape(B, 18, 128, 128), dv, test_cfg,
+                                grad_guide_fn=_RenderLoss.apply, langevin_noises=iter(lang))
     rel = _rel_l2(code_gpu.reshape(B, 18, 128, 128), ref)
-    assert rel < 2e-2, rel
+    print('guided ddim (through_unet=%s) rel l2 %.3e' % (through_unet, rel))
+    assert rel < 3e-3, rel
     # guidance actually moved the sample: the unguided run differs by much more than the tolerance
-    model.loss, model.update_extra_state, model.diffusion.p_sample_langevin = orig_loss, orig_ues, orig_lang
+    model.loss, model.update_extra_state = orig_loss, orig_ues
     cfg0 = dict(test_cfg, langevin_steps=0)
     model.diffusion.test_cfg = cfg0
     plain = model.diffusion(noise.reshape(B, 18, 128, 128).to(cuda), return_loss=False)
