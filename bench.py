@@ -7,14 +7,20 @@
 Workload (BASELINE.json configs[1]): `ssdnerf_cars_uncond`, batch 16 scenes per GPU, one STEP =
     50-step DDIM sample of a (3,6,128,128) triplane batch  ->  8-iteration occupancy-grid build  ->
     251-view 128x128 render of every scene (4.1 M rays per scene),
-random-init weights of the shipped architecture (UNet convs re-drawn N(0, 0.02) because the reference zero-inits
-half of them), synthetic noise and a synthetic 251-pose camera orbit.  Scenes are independent, so N GPUs run N
-independent batches (weak scaling, no data-path collective; the only exchange is the eval-side image all-gather).
+model built from the REFERENCE's own config (tests/golden/reference_configs.json = configs/paper_cfgs/ssdnerf_cars_uncond.py resolved),
+random-init weights (UNet convs re-drawn N(0, 0.02) because the reference zero-inits half of them), synthetic noise and a synthetic
+251-pose camera orbit.  Scenes are independent, so N GPUs run N independent batches (weak scaling); the one exchange of the reference's
+eval path -- the per-batch all-gather of lib/apis/test.py:41-53 -- runs on NCCL inside `e2e` at N > 1 (8-bit images, side stream,
+overlapped with the next batch's DDIM).
 
 `value`   = rays/s of the render stage, inputs resident in HBM (CUDA events on the launching stream, max over ranks)
 `triplanes_per_sec` = batch / DDIM-stage time, same measurement
-`e2e`     = the same step through the public plugin API (`DiffusionNeRF.val_step`) with PINNED HOST inputs and a
-            device->host read of the rendered images inside the timed region; e2e.value = rays / whole-step time.
+`e2e`     = the same step through the public plugin API (`DiffusionNeRF.val_step`) with PINNED HOST inputs, the device->host read of
+            the rendered images and (N > 1) the NCCL all-gather inside the timed region; e2e.value = rays / whole-step time.
+`render_variant_S` = north_star's synthetic workload (random-init 3x32x128x128 triplanes, class-default decoder, 251 views), every rank
+`strong_scaling`   = ONE scene x 251 views sharded by view over the N ranks (broadcast planes + bitfield, gather the images)
+`guided`           = config-4 shape (8 scenes, one 128x128 conditioning view): guided evaluations/s (UNet fwd + render loss fwd/bwd +
+                     UNet input-gradient pass), rank 0
 """
 import argparse
 import json
@@ -109,11 +115,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------- this repo
-def build_model(dev, seed=0):
+def reference_config(rel):
+    """a config of the reference, resolved by tests/golden/make_config_fixtures.py (the GPU box has no /root/reference)"""
+    return json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reference_configs.json')))[rel]
+
+
+def build_model(dev, seed=0, rel='configs/paper_cfgs/ssdnerf_cars_uncond.py', test_cfg_update=None):
     import ssdnerf_b200 as S
-    cfg = S.Config.fromfile(os.path.join(ROOT, 'configs', 'cars_uncond_b200.py'))
+    cfg = reference_config(rel)
+    test_cfg = dict(cfg['test_cfg'])
+    test_cfg.update(test_cfg_update or {})
     torch.manual_seed(seed)
-    model = S.build_model(cfg.model, test_cfg=cfg.test_cfg)
+    model = S.build_model(cfg['model'], train_cfg=cfg['train_cfg'], test_cfg=test_cfg)
     g = torch.Generator().manual_seed(seed)
     for mod in (model.diffusion_ema.denoising, model.diffusion.denoising):
         for name, p in mod.named_parameters():
@@ -122,17 +135,32 @@ def build_model(dev, seed=0):
     return model.to(dev).eval(), cfg
 
 
+def measured_traffic(kernel, rays):
+    """DRAM bytes per launch of `kernel` from a committed `ncu --set full` capture of this bench command (profiles/r02_render_traffic.json,
+    written by scripts/ncu_traffic.py from the .ncu-rep next to it); scaled by ray count when the capture used fewer views.  None when no
+    capture of the current kernel is committed -- never a hard-coded constant."""
+    path = os.path.join(ROOT, 'profiles', 'r02_render_traffic.json')
+    if not os.path.exists(path):
+        return None, None
+    d = json.load(open(path)).get(kernel)
+    if not d:
+        return None, None
+    return d['dram_bytes_per_launch'] * (rays / d['rays_per_launch']), f"profiles/r02_render_traffic.json ({d['source']})"
+
+
 def run_ours(args):
+    import ctypes
     import ssdnerf_b200 as S
     from ssdnerf_b200 import _lib as N
+    from ssdnerf_b200 import density as Dm
     from ssdnerf_b200 import renderer as R
+    import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device; the hot path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     model, cfg = build_model(dev, seed=0)
     diffusion, decoder = model.diffusion_ema, model.decoder_ema
@@ -143,11 +171,29 @@ def run_ours(args):
     intr_host = torch.tensor([131.25, 131.25, 64.0, 64.0]).expand(B, V, 4).contiguous().pin_memory()
     rays = B * V * IMG * IMG
     L = N.lib()
-    L.ssdnerf_launch_count.restype = __import__('ctypes').c_ulonglong
+    L.ssdnerf_launch_count.restype = ctypes.c_ulonglong
 
     noise, poses, intr = noise_host.to(dev), poses_host.to(dev), intr_host.to(dev)
     stream = torch.cuda.current_stream(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        """`steps` calls of fn between CUDA events on the launching stream, barrier + synchronize on both sides -> ms per call"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record(stream)
+        for _ in range(steps):
+            fn()
+        t1.record(stream)
+        barrier()
+        return t0.elapsed_time(t1) / steps
 
     def resident_step(rec=None):
         """one step with inputs already in HBM; stage boundaries marked with CUDA events on the launching stream"""
@@ -163,28 +209,45 @@ def run_ours(args):
             rec.append(e)
         return img
 
+    # ---- end-to-end through the plugin API with host buffers (+ the eval-side NCCL all-gather of 8-bit images when N > 1)
     out_host = torch.empty(B, V, 3, IMG, IMG, dtype=torch.float32).pin_memory()
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    u8_bufs = [torch.empty(B * V, 3, IMG, IMG, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    gathered = [torch.empty(world * B * V, 3, IMG, IMG, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    e2e_state = dict(i=0)
 
     def e2e_step():
-        """public API with host buffers: H2D inputs, val_step, D2H of the rendered images (lib/apis/test.py:27-53 data flow)"""
+        """public API with host buffers: H2D inputs, val_step, D2H of the rendered images (lib/apis/test.py:27-53 data flow); at N > 1 the
+        batch's images are quantised to 8 bits and all-gathered over NCCL on a side stream, overlapping the next batch's DDIM"""
         data = dict(scene_id=list(range(B)), scene_name=[str(i) for i in range(B)], noise=noise_host.to(dev, non_blocking=True),
                     test_poses=poses_host.to(dev, non_blocking=True), test_intrinsics=intr_host.to(dev, non_blocking=True))
         out = model.val_step(data)
+        if world > 1:
+            k = e2e_state['i'] & 1
+            e2e_state['i'] += 1
+            if pending[k] is not None:
+                pending[k].wait()                      # the gather that last used this buffer pair
+            u8_bufs[k].copy_((out['pred_imgs'].reshape(B * V, 3, IMG, IMG) * 255.0 + 0.5).to(torch.uint8))
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                pending[k] = dist.all_gather_into_tensor(gathered[k], u8_bufs[k], async_op=True)
         out_host.copy_(out['pred_imgs'], non_blocking=True)
         return out
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def e2e_drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+        if side is not None:
+            stream.wait_stream(side)
 
     # ---- resident (kernel-side) measurement
     for _ in range(args.warmup):
         resident_step()
     barrier()
     launches0 = L.ssdnerf_launch_count()
-    replays_per_step = DDIM_STEPS
     clocks = ClockSampler(local); clocks.start()
     rec = []
     t0, t1 = ev(), ev()
@@ -201,16 +264,17 @@ def run_ours(args):
     launches_api = (L.ssdnerf_launch_count() - launches0) / args.steps
     # kernels inside the replayed CUDA graph are launched by the driver: count the graph's kernel nodes once per replay
     graph_nodes = getattr(diffusion, '_graph_kernel_nodes', 0)
-    gpu_launches = int(launches_api + graph_nodes * (replays_per_step - 1))
+    gpu_launches = int(launches_api + graph_nodes * (DDIM_STEPS - 1))
 
-    # ---- end-to-end through the plugin API with host buffers
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
+    e2e_drain()
     barrier()
     s0, s1 = ev(), ev()
     s0.record(stream)
     for _ in range(args.steps):
         e2e_step()
+    e2e_drain()                                        # the last gather completes inside the timed region
     s1.record(stream)
     barrier()
     e2e_ms = s0.elapsed_time(s1) / args.steps
@@ -223,102 +287,151 @@ def run_ours(args):
                        img_hw=(IMG, IMG), want_blend=False)['num_samples']
     samples = int(cnt.sum().item())
 
-    # ---- side measurement (not part of the timed step): north_star's synthetic "random-init 3x32x128x128 triplane" workload through the
-    # class-default decoder (variant S: hidden 128, colour net 144 -> 128 -> 3), 32 views x 128^2 per scene, this rank's GPU only
-    side_S = None
-    if args.side_s and rank == 0:
+    # ---- north_star's synthetic workload on EVERY rank: random-init 3x32x128x128 triplanes through the class-default decoder (variant S:
+    # base 96 -> 128, colour net 144 -> 128 -> 3, xavier weights / zero bias as constructed), occupancy grid built by get_density, V views
+    s_ms = s_samples = None
+    if args.side_s:
         dec_s = S.build_module(dict(type='TriPlaneDecoder', max_steps=256)).to(dev).eval()
-        with torch.no_grad():
-            dec_s.density_net[0].bias += 1.0
-        gs = torch.Generator().manual_seed(77)
-        code_s = (torch.randn(B, 3, 32, 128, 128, generator=gs) * 0.5).to(dev)
-        vs = R.DEC_S
-        planes_s = R.pack_planes(code_s, vs)
-        from ssdnerf_b200 import density as Dm
-        _, bits_s = Dm.get_density(vs, planes_s, (128, 128), dec_s.packed_blob(), B, density_thresh=0.1, grid_size=64, bound=1.0)
-        Vs = min(32, V)
+        gs = torch.Generator().manual_seed(77 + rank)
+        code_s = torch.randn(B, 3, 32, 128, 128, generator=gs).clamp(-2, 2).to(dev)
+        planes_s = R.pack_planes(code_s, R.DEC_S)
+        _, bits_s = Dm.get_density(R.DEC_S, planes_s, (128, 128), dec_s.packed_blob(), B, density_thresh=0.1, grid_size=64, bound=1.0)
 
         def render_s(counts=False):
-            return R.render_fwd(vs, planes_s, (128, 128), bits_s, dec_s.packed_blob(), poses=poses[:, :Vs].contiguous(),
-                                intrinsics=intr[:, :Vs].contiguous(), img_hw=(IMG, IMG), want_blend=True, want_counts=counts)
-        for _ in range(2):
-            render_s()
-        torch.cuda.synchronize(dev)
-        a0, a1 = ev(), ev()
-        a0.record(stream)
-        for _ in range(3):
-            render_s()
-        a1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms_s = a0.elapsed_time(a1) / 3
-        n_s = int(render_s(True)['num_samples'].sum().item())
-        rays_s = B * Vs * IMG * IMG
-        side_S = {'workload': f'random-init 3x32x128x128 triplanes, class-default decoder (variant S), {B} scenes x {Vs} views x {IMG}x{IMG}, 1 GPU',
-                  'rays_per_sec': rays_s / (ms_s * 1e-3), 'samples_per_sec': n_s / (ms_s * 1e-3), 'ms': ms_s, 'samples_per_ray': n_s / rays_s,
-                  'kernel': 'k_render_s2 (fp16 planes, warp-level mma.sync MLP)', 'flops_per_sample': 62464,
-                  'tflops': n_s * 62464 / (ms_s * 1e-3) / 1e12}
+            return R.render_fwd(R.DEC_S, planes_s, (128, 128), bits_s, dec_s.packed_blob(), poses=poses, intrinsics=intr, img_hw=(IMG, IMG),
+                                want_blend=True, want_counts=counts)
+        s_ms = timed(render_s, max(1, min(args.steps, 3)), 1)
+        s_samples = int(render_s(True)['num_samples'].sum().item())
+        del code_s, planes_s
+
+    # ---- strong scaling (SURVEY.md §8e secondary): ONE scene x V views, views sharded over the ranks; rank 0 owns the scene and
+    # broadcasts code + bitfield (1.2 MB + 32 KB), every rank renders its contiguous view range, 8-bit images are all-gathered
+    code1 = code[:1].contiguous()
+    bits1 = bitfield[:1].contiguous()
+    v_lo, v_hi = (V * rank) // world, (V * (rank + 1)) // world
+    v_max = max((V * (r + 1)) // world - (V * r) // world for r in range(world))
+    my_poses, my_intr = poses[:1, v_lo:v_hi].contiguous(), intr[:1, v_lo:v_hi].contiguous()
+    ss_u8 = torch.zeros(v_max, IMG, IMG, 3, dtype=torch.uint8, device=dev)
+    ss_all = torch.empty(world * v_max, IMG, IMG, 3, dtype=torch.uint8, device=dev)
+
+    def strong_step():
+        if world > 1:
+            dist.broadcast(code1, 0)
+            dist.broadcast(bits1, 0)
+        img, _ = model.render(decoder, code1, bits1, IMG, IMG, my_intr, my_poses, cfg=model.test_cfg)
+        ss_u8[:v_hi - v_lo].copy_((img[0].clamp(0, 1) * 255.0 + 0.5).to(torch.uint8))
+        if world > 1:
+            dist.all_gather_into_tensor(ss_all, ss_u8)
+    strong_ms = timed(strong_step, 10, 3)
+
+    # ---- config-4 shape guided evaluations (rank 0): UNet forward + render loss forward/backward + UNet input-gradient pass
+    guided = None
+    if args.guided and rank == 0:
+        guided = guided_measurement(dev, ev, stream)
 
     # ---- reduce over ranks (max time)
-    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms], device=dev, dtype=torch.float64)
-    samples_t = torch.tensor([samples], device=dev, dtype=torch.float64)
+    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms or 0.0, strong_ms], device=dev, dtype=torch.float64)
+    sums = torch.tensor([samples, s_samples or 0], device=dev, dtype=torch.float64)
     if world > 1:
-        import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(samples_t, op=dist.ReduceOp.SUM)
-    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms = [float(x) for x in times.tolist()]
-    samples_all = float(samples_t.item())
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms_all, strong_ms = [float(x) for x in times.tolist()]
+    samples_all, s_samples_all = [float(x) for x in sums.tolist()]
     if rank != 0:
         if world > 1:
-            import torch.distributed as dist
             dist.destroy_process_group()
         return
     pk = peaks()
     rays_all, trip_all = rays * world, B * world
     rays_per_s = rays_all / (rend_ms * 1e-3)
     trip_per_s = trip_all / (ddim_ms * 1e-3)
-    # roofline of the dominant kernel of the step (the DDIM stage is > 80 % of the step): tcgen05 implicit-GEMM conv
     unet_flops = UNET_FLOP_PER_SAMPLE_STEP * B * DDIM_STEPS            # per rank per step
     tf_achieved = unet_flops / (ddim_ms * 1e-3) / 1e12
     render_bytes = (samples_all / world) * RAY_GATHER_BYTES_PER_SAMPLE + rays * RAY_IO_BYTES
+    kern_p = os.environ.get('SSDNERF_BENCH_KERNEL_P', 'k_render_p2')
+    traffic, traffic_src = measured_traffic(kern_p, rays)
+    gather_bytes = B * V * IMG * IMG * 3 * world if world > 1 else 0
     line = {
         'metric': METRIC, 'value': rays_per_s, 'unit': 'rays/s', 'triplanes_per_sec': trip_per_s,
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp16 tensor-core UNet (fp32 accumulate), fp32 renderer', 'data': 'synthetic',
-        'config': {'workload': f'ssdnerf_cars_uncond: {DDIM_STEPS}-step DDIM + 8-iter density grid + {V}-view {IMG}x{IMG} render, '
-                               f'batch {B}/GPU', 'global_batch': trip_all, 'rays_per_step': rays_all, 'samples_per_ray': samples_all / rays_all,
-                   'parallelism': f'scenes x{world} (independent replicas, no data-path collective)',
+        'config': {'workload': f'ssdnerf_cars_uncond (reference config, resolved): {DDIM_STEPS}-step DDIM + 8-iter density grid + {V}-view '
+                               f'{IMG}x{IMG} render, batch {B}/GPU', 'global_batch': trip_all, 'rays_per_step': rays_all,
+                   'samples_per_ray': samples_all / rays_all,
+                   'parallelism': f'scenes x{world} (independent replicas; e2e adds the eval-side NCCL all-gather of 8-bit images)',
                    'l2_policy': 'working set per step (activations > 1 GB, 66 M rays of output) exceeds the 126 MB L2; no flush needed'},
         'stage_ms': {'ddim': ddim_ms, 'density': dens_ms, 'render': rend_ms},
-        'e2e': {'value': rays_all / (e2e_ms * 1e-3), 'unit': 'rays/s (whole val_step: H2D + DDIM + density + render + D2H)',
-                'triplanes_per_sec': trip_all / (e2e_ms * 1e-3), 'ms_per_step': e2e_ms,
+        'e2e': {'value': rays_all / (e2e_ms * 1e-3), 'unit': 'rays/s', 'triplanes_per_sec': trip_all / (e2e_ms * 1e-3), 'ms_per_step': e2e_ms,
+                'path': 'DiffusionNeRF.val_step: H2D (noise, poses, intrinsics) + DDIM + density + render + D2H of the images'
+                        + (' + NCCL all-gather of the 8-bit images (side stream, overlapped with the next DDIM)' if world > 1 else ''),
                 'h2d_bytes_per_step': int(noise_host.numel() * 4 + poses_host.numel() * 4 + intr_host.numel() * 4),
-                'd2h_bytes_per_step': int(out_host.numel() * 4)},
+                'd2h_bytes_per_step': int(out_host.numel() * 4), 'nccl_allgather_bytes_per_rank_per_step': int(gather_bytes)},
         'gpu_launches': gpu_launches,
         'clocks': clk,
-        # dominant kernel of the step = the fused renderer (k_render_p2, ~64 % of the step): algorithmic gather + output bytes per
-        # launch / launch duration against the measured HBM copy peak; `traffic` = DRAM bytes of the same kernel from
-        # the committed ncu capture scaled to this launch -- the planes (1.5 MB/scene) are L2-resident, so real DRAM traffic is ~ the
-        # 20 B/ray output and the binding unit is the SM (MUFU / issue), see profiles/r01_ncu_prof_render_P_MMA.txt
-        'roofline': {'kernel': 'k_render_p2 (fused march + gather + MLP + composite), one launch per step', 'bound': 'hbm',
+        # dominant kernel of the step = the fused renderer (~3/4 of the step): ALGORITHMIC gather + output bytes per launch / launch
+        # duration against the measured HBM copy peak.  The planes (1.5 MB/scene) are L1/L2-resident, so real DRAM
+        # traffic (`traffic`, from the committed ncu capture) is far below the algorithmic bytes and the binding unit is the SM.
+        'roofline': {'kernel': f'{kern_p} (fused march + gather + MLP + composite), one launch per step', 'bound': 'hbm',
                      'achieved': render_bytes / (rend_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                      'frac': render_bytes / (rend_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'peak_source': pk['src'] + ' (burst copy)',
-                     'algorithmic_bytes_per_launch': render_bytes, 'traffic': rays * 12.4 + 16 * 1.6e6,
-                     'traffic_note': 'ncu dram__bytes (read+write) of k_render_p2: 12.4 B/ray + plane/bitfield first touch; gather is served by L1/L2'},
-        'roofline_unet': {'kernel': 'k_gemm_tc (tcgen05 implicit-GEMM conv / GEMM) + glue, timed as the whole DDIM stage', 'bound': 'tensor',
+                     'algorithmic_bytes_per_launch': render_bytes, 'samples_per_sec': samples_all / world / (rend_ms * 1e-3),
+                     'traffic': traffic, 'traffic_source': traffic_src},
+        'roofline_unet': {'kernel': 'k_gemm_tc / k_conv_row2 (tcgen05 implicit-GEMM conv / GEMM) + glue, timed as the whole DDIM stage', 'bound': 'tensor',
                           'achieved': tf_achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s', 'frac': tf_achieved / pk['tf_sustained'],
-                          'peak_source': f"{pk['src']} (sustained cuBLAS bf16)",
-                          'note': 'per-layer table: profiles/r01_unet_layer_table.txt (128x128- and 64x64-level convs 1.0-1.5 PFLOP/s; the operand '
-                                  'pipeline of one SM saturates at ~58 B/clk, profiles/r01_gemm_pipeline_prof.txt); GroupNorm-apply passes, '
-                                  'attention and the latency-bound 8x8/16x16 levels pull the stage average down'},
+                          'peak_source': f"{pk['src']} (sustained cuBLAS bf16)"},
+        'strong_scaling': {'workload': f'1 scene x {V} views x {IMG}x{IMG}, views sharded over {world} rank(s); per call: broadcast code + bitfield '
+                                       f'from rank 0, render, all-gather 8-bit images' if world > 1 else f'1 scene x {V} views x {IMG}x{IMG} on one GPU',
+                           'ms': strong_ms, 'rays_per_sec': V * IMG * IMG / (strong_ms * 1e-3), 'scaling': 'strong'},
     }
-    if side_S is not None:
-        line['render_variant_S'] = side_S
+    if s_ms is not None:
+        rays_s = B * V * IMG * IMG * world
+        line['render_variant_S'] = {
+            'workload': f'random-init 3x32x128x128 triplanes (clamped N(0,1)), class-default TriPlaneDecoder (variant S), {B} scenes x {V} views x '
+                        f'{IMG}x{IMG} per GPU, occupancy grid from get_density(thresh 0.1)', 'n_gpus': world,
+            'rays_per_sec': rays_s / (s_ms_all * 1e-3), 'samples_per_sec': s_samples_all / (s_ms_all * 1e-3), 'ms': s_ms_all,
+            'samples_per_ray': s_samples_all / rays_s, 'kernel': os.environ.get('SSDNERF_BENCH_KERNEL_S', 'k_render_s2'),
+            'flops_per_sample': 62464, 'tflops': s_samples_all * 62464 / (s_ms_all * 1e-3) / 1e12 / world,
+            'roofline': {'bound': 'hbm', 'algorithmic_bytes_per_sample': 768,
+                         'achieved': (s_samples_all / world * 768 + rays * RAY_IO_BYTES) / (s_ms_all * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': (s_samples_all / world * 768 + rays * RAY_IO_BYTES) / (s_ms_all * 1e-3) / 1e9 / pk['hbm_gbs']}}
+    if guided is not None:
+        line['guided'] = guided
     if args.cpu_baseline and world == 1:          # reported baseline: rank 0 at N = 1 only
         line['cpu_baseline'] = cpu_reference_sample(quick=True)
     print(json.dumps(line))
     if world > 1:
-        import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def guided_measurement(dev, ev, stream, scenes=8, evals=6):
+    """BASELINE config 4 (`ssdnerf_chairs_recons1v`, reference config resolved): `evals` guided x_0 predictions at 8 scenes x one 128x128
+    conditioning view = what every DDIM / langevin step of val_guide costs (445 of them per batch in the shipped config)."""
+    model, _ = build_model(dev, seed=1, rel='configs/paper_cfgs/ssdnerf_chairs_recons1v.py')
+    diffusion, decoder = model.diffusion_ema, model.decoder_ema
+    g = torch.Generator().manual_seed(5)
+    code0 = (torch.randn(scenes, 3, 6, 128, 128, generator=g) * 0.5).to(dev)
+    poses = orbit_poses(4)[None].repeat(scenes, 1, 1, 1)[:, :1].contiguous().to(dev)
+    intr = torch.tensor([131.25, 131.25, 64.0, 64.0]).expand(scenes, 1, 4).contiguous().to(dev)
+    with torch.no_grad():
+        _, bits0 = model.get_density(decoder, code0, cfg=dict(density_thresh=0.1))
+        img0, _ = model.render(decoder, code0, bits0, IMG, IMG, intr, poses, cfg=model.test_cfg)
+    data = dict(cond_imgs=img0, cond_intrinsics=intr, cond_poses=poses, noise=torch.randn(scenes, 3, 6, 128, 128, generator=g).to(dev))
+    # time `evals` guided evaluations through the public sampler: num_timesteps = evals, no langevin
+    model.test_cfg.update(num_timesteps=evals, langevin_steps=0)
+    diffusion.test_cfg.update(num_timesteps=evals, langevin_steps=0)
+    model.val_guide(data)                                  # warm-up (packs the transposed weights, sizes the scratch)
+    torch.cuda.synchronize(dev)
+    a, b = ev(), ev()
+    a.record(stream)
+    model.val_guide(data)
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / evals
+    return {'workload': f'ssdnerf_chairs_recons1v (reference config): {scenes} scenes, 1 cond view {IMG}x{IMG}, grad_through_unet (default), '
+                        f'{evals} guided evaluations via val_guide', 'ms_per_guided_eval': ms, 'guided_evals_per_sec': 1e3 / ms,
+            'rays_fwd_bwd_per_sec': scenes * IMG * IMG / (ms * 1e-3),
+            'unet_fwd_bwd_tflops': 3 * UNET_FLOP_PER_SAMPLE_STEP * scenes / (ms * 1e-3) / 1e12,
+            'note': 'flops = forward + data-gradient pass (2x forward) of the UNet only; includes the occupancy update and the fused render loss'}
 
 
 # ----------------------------------------------------------------------------------------------------------- reference arm
@@ -403,7 +516,8 @@ def main():
     ap.add_argument('--batch', type=int, default=B_PER_GPU)
     ap.add_argument('--views', type=int, default=NUM_VIEWS)
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
-    ap.add_argument('--no-side-s', dest='side_s', action='store_false', help='skip the variant-S renderer side measurement')
+    ap.add_argument('--no-side-s', dest='side_s', action='store_false', help='skip the variant-S renderer workload')
+    ap.add_argument('--no-guided', dest='guided', action='store_false', help='skip the config-4 guided-evaluation measurement')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3      # timing rule: at least 3 warm-up steps
