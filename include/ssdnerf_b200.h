@@ -97,8 +97,10 @@ SSDNERF_API int ssdnerf_sh_encode_backward(const float* grad, const float* input
                            (configs/paper_cfgs/ssdnerf_cars_uncond.py:40-51) */
 #define SSDNERF_DEC_P_SIMT 2 /* decoder P on the CUDA cores in plain fp32 (csrc/render_fused.cu) */
 #define SSDNERF_DEC_P_TC 3   /* decoder P with the base layer as a split-precision fp16 tcgen05 GEMM (csrc/render_ptc.cu);
-                                SSDNERF_DEC_P selects the fastest P kernel (currently SSDNERF_DEC_P_MMA) */
+                                SSDNERF_DEC_P selects the fastest P kernel (currently SSDNERF_DEC_P_MMA2) */
 #define SSDNERF_DEC_P_MMA 4  /* decoder P, warp-synchronous: per-warp split-precision mma.sync base layer (csrc/render_p2.cu) */
+#define SSDNERF_DEC_P_MMA2 7 /* decoder P, warp-synchronous v2: one exponential per hidden unit shared by both branches, dir_net on the
+                                tensor cores, one reciprocal per four sigmoids (csrc/render_p3.cu); what SSDNERF_DEC_P selects */
 #define SSDNERF_DEC_S_TC 6   /* decoder S, CTA-synchronous tcgen05 kernel (csrc/render_tc.cu) */
 #define SSDNERF_DEC_S_MMA 5  /* decoder S, warp-synchronous mma.sync kernel (csrc/render_s2.cu); SSDNERF_DEC_S selects the faster one */
 #define SSDNERF_DEC_S 1 /* TriPlaneDecoder class defaults: base 3*32->128, density 128->1, color (128+16)->128->3

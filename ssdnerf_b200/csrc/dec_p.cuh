@@ -24,6 +24,16 @@ struct BitfieldLoader {
     __device__ __forceinline__ uint32_t operator()(uint32_t byte) const { return __ldg(g + byte); }
 };
 
+// one 32-byte texel (8 floats, 6 used) as ONE 256-bit read-only load (LDG.E.256, sm_100): half the load instructions and half the
+// L1 wavefronts of two 128-bit loads -- the gather is the main client of the L1 data pipe (profiles/r02_render_p_analysis.txt)
+struct Texel8 { float4 lo, hi; };
+__device__ __forceinline__ Texel8 ldg_texel8(const float* __restrict__ p) {
+    Texel8 t;
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(t.lo.x), "=f"(t.lo.y), "=f"(t.lo.z), "=f"(t.lo.w), "=f"(t.hi.x), "=f"(t.hi.y), "=f"(t.hi.z), "=f"(t.hi.w) : "l"(p));
+    return t;
+}
+
 // bilinear gather of one plane, fp32 channels-last with 8 floats per texel (6 used)
 __device__ __forceinline__ void gather_plane_p(const float* __restrict__ plane, uint32_t Hp, uint32_t Wp,
                                                float u, float v, float* __restrict__ f) {
@@ -37,14 +47,9 @@ __device__ __forceinline__ void gather_plane_p(const float* __restrict__ plane, 
     const int x1 = min(x0 + 1, (int)Wp - 1), y1 = min(y0 + 1, (int)Hp - 1);
     const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.0f) - ix, wy0 = (fy0 + 1.0f) - iy;
     const float nw = wx0 * wy0, ne = wx1 * wy0, sw = wx0 * wy1, se = wx1 * wy1;
-    const float4* p00 = reinterpret_cast<const float4*>(plane + ((size_t)y0 * Wp + x0) * 8);
-    const float4* p01 = reinterpret_cast<const float4*>(plane + ((size_t)y0 * Wp + x1) * 8);
-    const float4* p10 = reinterpret_cast<const float4*>(plane + ((size_t)y1 * Wp + x0) * 8);
-    const float4* p11 = reinterpret_cast<const float4*>(plane + ((size_t)y1 * Wp + x1) * 8);
-    const float4 a0 = __ldg(p00), a1 = __ldg(p00 + 1);
-    const float4 b0 = __ldg(p01), b1 = __ldg(p01 + 1);
-    const float4 c0 = __ldg(p10), c1 = __ldg(p10 + 1);
-    const float4 d0 = __ldg(p11), d1 = __ldg(p11 + 1);
+    const Texel8 ta = ldg_texel8(plane + ((size_t)y0 * Wp + x0) * 8), tb = ldg_texel8(plane + ((size_t)y0 * Wp + x1) * 8);
+    const Texel8 tc = ldg_texel8(plane + ((size_t)y1 * Wp + x0) * 8), td = ldg_texel8(plane + ((size_t)y1 * Wp + x1) * 8);
+    const float4 a0 = ta.lo, a1 = ta.hi, b0 = tb.lo, b1 = tb.hi, c0 = tc.lo, c1 = tc.hi, d0 = td.lo, d1 = td.hi;
     f[0] = a0.x * nw + b0.x * ne + c0.x * sw + d0.x * se;
     f[1] = a0.y * nw + b0.y * ne + c0.y * sw + d0.y * se;
     f[2] = a0.z * nw + b0.z * ne + c0.z * sw + d0.z * se;

@@ -67,6 +67,9 @@ int render_ptc_launch(const RenderParams& p, int emulate_schedule, uint32_t* his
 // variant P, warp-level mma.sync (render_p2.cu)
 int render_p2_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream);
 
+// variant P, warp-level mma.sync, shared exponentials + tensor-core dir_net (render_p3.cu)
+int render_p3_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream);
+
 // variant S, warp-level mma.sync (render_s2.cu)
 int render_s2_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream);
 

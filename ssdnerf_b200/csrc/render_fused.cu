@@ -262,14 +262,14 @@ using namespace ssdnerf;
 extern "C" {
 
 size_t ssdnerf_decoder_blob_floats(int variant) {
-    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) return DecP::BLOB;
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA || variant == SSDNERF_DEC_P_MMA2) return DecP::BLOB;
     if (variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC) return ssdnerf::dec_s_blob_floats();
     return 0;
 }
 
 size_t ssdnerf_planes_bytes(int variant, uint32_t B, uint32_t Hp, uint32_t Wp) {
     const size_t texels = (size_t)B * 3 * Hp * Wp;
-    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) return texels * 8 * sizeof(float);
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA || variant == SSDNERF_DEC_P_MMA2) return texels * 8 * sizeof(float);
     if (variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC) return texels * 32 * sizeof(__half);
     return 0;
 }
@@ -278,9 +278,9 @@ int ssdnerf_pack_planes(int variant, const float* code, uint32_t B, uint32_t C, 
                         void* stream) {
     const size_t total = (size_t)B * 3 * Hp * Wp;
     if (total == 0) return 0;
-    if (((uintptr_t)planes & 15u) != 0) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: planes must be 16-byte aligned");
+    if (((uintptr_t)planes & 31u) != 0) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: planes must be 32-byte aligned (256-bit texel loads)");
     const uint32_t blocks = (uint32_t)((total + 255) / 256);
-    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA) {
+    if (variant == SSDNERF_DEC_P || variant == SSDNERF_DEC_P_SIMT || variant == SSDNERF_DEC_P_TC || variant == SSDNERF_DEC_P_MMA || variant == SSDNERF_DEC_P_MMA2) {
         if (C != 6) return set_error_msg(SSDNERF_ERR_ARG, "pack_planes: variant P expects 6 channels per plane");
         k_pack_planes<float, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(code, B, C, Hp, Wp, (float*)planes);
     } else if (variant == SSDNERF_DEC_S || variant == SSDNERF_DEC_S_MMA || variant == SSDNERF_DEC_S_TC) {
@@ -351,7 +351,8 @@ int ssdnerf_render_fwd(const ssdnerf_render_args* a, void* stream_) {
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
     if (a->variant == SSDNERF_DEC_P_TC) return ssdnerf::render_ptc_launch(p, a->emulate_schedule, hist, sms, stream);
-    if (a->variant == SSDNERF_DEC_P_MMA || a->variant == SSDNERF_DEC_P) return ssdnerf::render_p2_launch(p, a->emulate_schedule, hist, sms, stream);
+    if (a->variant == SSDNERF_DEC_P_MMA) return ssdnerf::render_p2_launch(p, a->emulate_schedule, hist, sms, stream);
+    if (a->variant == SSDNERF_DEC_P_MMA2 || a->variant == SSDNERF_DEC_P) return ssdnerf::render_p3_launch(p, a->emulate_schedule, hist, sms, stream);
     if (a->variant == SSDNERF_DEC_P_SIMT) {
         // two register budgets of the same kernel: 3 CTAs/SM (168 regs, no spills) or 4 CTAs/SM (128 regs, small spills);
         // SSDNERF_P_OCC=3|4 overrides the default for A/B runs

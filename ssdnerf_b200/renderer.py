@@ -15,7 +15,8 @@ DEC_P_TC = 3     # DEC_P with a split-precision tcgen05 base layer
 DEC_P_MMA = 4    # DEC_P, warp-synchronous split-precision mma.sync base layer
 DEC_S_MMA = 5    # DEC_S, warp-synchronous mma.sync kernel
 DEC_S_TC = 6     # DEC_S, CTA-synchronous tcgen05 kernel
-_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6, DEC_P_MMA: 6, DEC_S_MMA: 32, DEC_S_TC: 32}
+DEC_P_MMA2 = 7   # DEC_P, warp-synchronous v2 (shared exponentials, tensor-core dir_net): what DEC_P selects
+_VARIANT_C = {DEC_P: 6, DEC_S: 32, DEC_P_SIMT: 6, DEC_P_TC: 6, DEC_P_MMA: 6, DEC_S_MMA: 32, DEC_S_TC: 32, DEC_P_MMA2: 6}
 
 
 def detect_variant(params):
@@ -43,7 +44,7 @@ def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cu
     if variant is None:
         variant = detect_variant(params)
     p = {k: v.detach().float().cpu() for k, v in params.items()}
-    if variant in (DEC_P, DEC_P_SIMT, DEC_P_TC, DEC_P_MMA):
+    if variant in (DEC_P, DEC_P_SIMT, DEC_P_TC, DEC_P_MMA, DEC_P_MMA2):
         w1 = _plane_major(p['base_net.0.weight'], 6).t().contiguous()           # [18][64], row k = plane*6+c
         parts = [w1.reshape(-1), p['base_net.0.bias'],
                  p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),

@@ -9,7 +9,7 @@ from tests.common import spiral_poses
 dev = torch.device('cuda:0')
 variant = sys.argv[1] if len(sys.argv) > 1 else 'P'
 B, V, res = int(os.environ.get('B', 16)), int(os.environ.get('V', 8)), 128
-vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'P_MMA': R.DEC_P_MMA, 'S': R.DEC_S, 'S_MMA': R.DEC_S_MMA, 'S_TC': R.DEC_S_TC}[variant]
+vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'P_MMA': R.DEC_P_MMA, 'P_MMA2': R.DEC_P_MMA2, 'S': R.DEC_S, 'S_MMA': R.DEC_S_MMA, 'S_TC': R.DEC_S_TC}[variant]
 C = 32 if variant[0] == 'S' else 6
 g = torch.Generator().manual_seed(0)
 code = torch.randn(B, 3, C, 128, 128, generator=g).clamp(-2, 2).to(dev)

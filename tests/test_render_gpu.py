@@ -41,12 +41,12 @@ def _run_gpu(variant, vid, params, code, bf, poses, intr, res, cuda, max_steps, 
     return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
 
 
-@pytest.mark.parametrize('variant', ['P', 'P_SIMT', 'P_TC', 'S', 'S_TC'])
+@pytest.mark.parametrize('variant', ['P', 'P_SIMT', 'P_TC', 'P_MMA', 'P_MMA2', 'S', 'S_TC'])
 @pytest.mark.parametrize('grid', ['ones', 'sphere'])
 def test_config1_explicit_rays(cuda, variant, grid):
     """64x64 render, max_steps=32 (fixed step dt_max), bit-exact integer trace."""
     from ssdnerf_b200 import renderer as R
-    vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'S': R.DEC_S, 'S_TC': R.DEC_S_TC}[variant]
+    vid = {'P': R.DEC_P, 'P_SIMT': R.DEC_P_SIMT, 'P_TC': R.DEC_P_TC, 'P_MMA': R.DEC_P_MMA, 'P_MMA2': R.DEC_P_MMA2, 'S': R.DEC_S, 'S_TC': R.DEC_S_TC}[variant]
     code, poses, intr = config1(variant[0])
     params = rp.make_decoder_params(variant[0], 0)
     bf = _bitfields()[grid]
