@@ -35,7 +35,7 @@ struct SmemP3 {
     alignas(16) uint8_t a_lo[kP3Warps][32 * kARow3];
     alignas(16) uint4 wfrag[8][2][32];                         // base layer: [n-tile][hi|lo][lane] = {b0,b1 of k-chunk 0, b0,b1 of k-chunk 1}
     alignas(16) uint4 dfrag[8][32];                            // dir_net: [n-tile][lane] = {b0,b1 hi, b0,b1 lo}, K = 16 SH values
-    ulonglong4 heads2[DecP::HID / 2];                          // per column pair: {wd, wc0, wc1, wc2} x (col, col+1) as f32x2, * (-ln 2)
+    float4 heads[DecP::HID];                                   // {wd, wc0, wc1, wc2}[col] * (-ln 2)
     float bd, bc[3], sat;
     alignas(16) float edf[kP3Warps][32 * kEdfStride];         // (EDF mode only; last member) edf[ray][col] = 2^(zf), zf = -log2(e) * dir_net(SH16(d))[col]
 };
@@ -58,17 +58,8 @@ __device__ __forceinline__ void mma_16816_p3(float* d, const uint32_t* a, uint32
 
 // EDF = true: exp(-f) table in shared memory, one ex2 per hidden unit (3 CTAs / SM by shared memory);
 // EDF = false: no table -- both exponentials evaluated, 33 KB of shared memory per CTA so occupancy is set by registers alone.
-// Blackwell packed fp32 (FFMA2 / FMUL2 / FADD2: one issue slot, two lanes of work).  The kernel is bound by instruction issue and
-// fixed-latency dependencies (ncu: IPC 0.6, top stalls wait / not-selected / mio-throttle), so the element-wise tail of the heads runs
-// on register pairs = the two adjacent columns an accumulator fragment holds.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
-template <int MINB, bool EDF>
+// ABL: timing-only ablations (SSDNERF_P3_ABLATE, wrong images): 1 = no transcendentals in the heads, 2 = no plane gather, 3 = no MMA, 4 = no probe arithmetic
+template <int MINB, bool EDF, int ABL>
 __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemP3& s = *reinterpret_cast<SmemP3*>(smem_raw);
@@ -117,16 +108,9 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
             }
             s.dfrag[nt][ln] = make_uint4(hi[0], hi[1], lo[0], lo[1]);
         }
-        for (int i = tid; i < DecP::HID / 2; i += kP3Threads) {   // silu(x) = x * sigma = (z / -log2 e) * sigma: fold -ln 2 into the heads
-            float* h = reinterpret_cast<float*>(&s.heads2[i]);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int c = 2 * i + e;
-                h[e] = -kLn2 * __ldg(blob + DecP::OFF_WD + c);
-                h[2 + e] = -kLn2 * __ldg(blob + DecP::OFF_WC + c);
-                h[4 + e] = -kLn2 * __ldg(blob + DecP::OFF_WC + DecP::HID + c);
-                h[6 + e] = -kLn2 * __ldg(blob + DecP::OFF_WC + 2 * DecP::HID + c);
-            }
+        for (int i = tid; i < DecP::HID; i += kP3Threads) {       // silu(x) = x * sigma = (z / -log2 e) * sigma: fold -ln 2 into the heads
+            s.heads[i] = make_float4(-kLn2 * __ldg(blob + DecP::OFF_WD + i), -kLn2 * __ldg(blob + DecP::OFF_WC + i),
+                                     -kLn2 * __ldg(blob + DecP::OFF_WC + DecP::HID + i), -kLn2 * __ldg(blob + DecP::OFF_WC + 2 * DecP::HID + i));
         }
         if (tid == 0) {
             s.bd = __ldg(blob + DecP::OFF_BD);
@@ -234,16 +218,22 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
             float x = 0.0f, y = 0.0f, z = 0.0f, dt = 0.0f; uint32_t vi = 0;
             while (alive && !has) {
                 if (!(t < far) || ns >= cap) { alive = false; break; }
-                has = probe(c, r, grid, t, x, y, z, dt, vi);
+                if (ABL == 4) { x = fmaf(t, r.dx, r.ox); y = fmaf(t, r.dy, r.oy); z = fmaf(t, r.dz, r.oz); dt = c.dt_min; vi = 0; has = true; }
+                else has = probe(c, r, grid, t, x, y, z, dt, vi);
             }
             if (!__any_sync(0xffffffffu, has)) break;
 
             // ---- phase 2: bilinear features of this lane's sample -> split fp16 row of the warp's A tile
             if (has) {
                 float f[DecP::KF];
-                gather_plane_p(planes, p.plane_h, p.plane_w, x, y, f);
-                gather_plane_p(planes + plane_stride, p.plane_h, p.plane_w, x, z, f + 6);
-                gather_plane_p(planes + 2 * plane_stride, p.plane_h, p.plane_w, y, z, f + 12);
+                if (ABL == 2) {
+#pragma unroll
+                    for (int q = 0; q < DecP::KF; ++q) f[q] = x * (float)q + y;
+                } else {
+                    gather_plane_p(planes, p.plane_h, p.plane_w, x, y, f);
+                    gather_plane_p(planes + plane_stride, p.plane_h, p.plane_w, x, z, f + 6);
+                    gather_plane_p(planes + 2 * plane_stride, p.plane_h, p.plane_w, y, z, f + 12);
+                }
                 uint4* rh = reinterpret_cast<uint4*>(s.a_hi[warp] + lane * kARow3);
                 uint4* rl = reinterpret_cast<uint4*>(s.a_lo[warp] + lane * kARow3);
 #pragma unroll
@@ -268,7 +258,7 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
                     ldmatrix_x4_p3(a_lo_base + mt * 16 * kARow3 + kc * 32 + ld_off, al[mt][kc]);
                 }
             // per-row partial head sums of this lane; rows g + 8*j, j = 0..3 (j = 2*mt + upper half)
-            f32x2 psd2[4] = {0ull, 0ull, 0ull, 0ull}, pr2[4] = {0ull, 0ull, 0ull, 0ull}, pg2[4] = {0ull, 0ull, 0ull, 0ull}, pb2[4] = {0ull, 0ull, 0ull, 0ull};
+            float psd[4] = {0.f, 0.f, 0.f, 0.f}, pr[4] = {0.f, 0.f, 0.f, 0.f}, pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int nt = 0; nt < 8; ++nt) {
                 const uint4 bh = s.wfrag[nt][0][lane], bl = s.wfrag[nt][1][lane];
@@ -277,6 +267,12 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.0f;
+                    if (ABL == 3) {
+                        d[mt][0] = __uint_as_float(ah[mt][0][0] ^ bh.x); d[mt][1] = __uint_as_float(al[mt][1][1] ^ bl.y);
+                        d[mt][2] = __uint_as_float(ah[mt][1][2] ^ bh.z); d[mt][3] = __uint_as_float(al[mt][0][3] ^ bl.w);
+                        dc[mt][0] = d[mt][1] + __uint_as_float(bd4.x); dc[mt][1] = d[mt][0]; dc[mt][2] = d[mt][3]; dc[mt][3] = d[mt][2] + __uint_as_float(asl[mt][0]);
+                        continue;
+                    }
                     mma_16816_p3(d[mt], al[mt][0], bh.x, bh.y);       // small terms first
                     mma_16816_p3(d[mt], al[mt][1], bh.z, bh.w);
                     mma_16816_p3(d[mt], ah[mt][0], bl.x, bl.y);
@@ -289,46 +285,37 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
                     mma_16816_p3(dc[mt], ash[mt], bd4.x, bd4.y);
                 }
                 const int col = nt * 8 + 2 * t4;
-                const ulonglong4 hw = s.heads2[col >> 1];           // {wd, wr, wg, wb} x (col, col + 1)
-                const f32x2 one2 = pk(1.0f, 1.0f);
+                const float4 hw0 = s.heads[col], hw1 = s.heads[col + 1];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float z0 = d[j >> 1][(j & 1) * 2], z1 = d[j >> 1][(j & 1) * 2 + 1];          // -log2(e) * b
-                    const float y0 = dc[j >> 1][(j & 1) * 2], y1 = dc[j >> 1][(j & 1) * 2 + 1];        // -log2(e) * (b + f)
-                    f32x2 sg12, sg34;                                                                  // sigmoids of (col, col+1): density, colour
-                    if (EDF) {
+                    float z0 = d[j >> 1][(j & 1) * 2], z1 = d[j >> 1][(j & 1) * 2 + 1];          // -log2(e) * b
+                    float y0 = dc[j >> 1][(j & 1) * 2], y1 = dc[j >> 1][(j & 1) * 2 + 1];        // -log2(e) * (b + f)
+                    float s0, s1, h0, h1;                                                         // z * sigmoid; the -ln 2 lives in the head weights
+                    if (ABL == 1) {            // ablation (timing only): no transcendental work
+                        s0 = fmaxf(z0, 0.f); s1 = fmaxf(z1, 0.f); h0 = fmaxf(y0, 0.f); h1 = fmaxf(y1, 0.f);
+                    } else if (EDF) {
                         // exp(-b) once per unit; exp(-(b + f)) = exp(-b) exp(-f); every factor clamped to 2^30 so the 4-way product is finite
-                        const f32x2 ef = *reinterpret_cast<const f32x2*>(edfw + (g + 8 * j) * kEdfStride + col);
-                        const f32x2 e2 = pk(ex2_approx(fminf(z0, 30.0f)), ex2_approx(fminf(z1, 30.0f)));
-                        float ey0, ey1;
-                        upk(mul2(e2, ef), ey0, ey1);
-                        float d1, d2, d3, d4;
-                        upk(add2(e2, one2), d1, d2);
-                        upk(add2(pk(fminf(ey0, 1073741824.0f), fminf(ey1, 1073741824.0f)), one2), d3, d4);
+                        const float2 ef = *reinterpret_cast<const float2*>(edfw + (g + 8 * j) * kEdfStride + col);
+                        const float e0 = ex2_approx(fminf(z0, 30.0f)), e1 = ex2_approx(fminf(z1, 30.0f));
+                        const float d1 = 1.0f + e0, d2 = 1.0f + e1;
+                        const float d3 = 1.0f + fminf(e0 * ef.x, 1073741824.0f), d4 = 1.0f + fminf(e1 * ef.y, 1073741824.0f);
                         const float p12 = d1 * d2, p34 = d3 * d4;
                         const float rr = rcp_approx(p12 * p34);
                         const float r12 = rr * p34, r34 = rr * p12;            // 1 / (d1 d2), 1 / (d3 d4)
-                        sg12 = pk(r12 * d2, r12 * d1); sg34 = pk(r34 * d4, r34 * d3);
+                        s0 = z0 * (r12 * d2); s1 = z1 * (r12 * d1);
+                        h0 = y0 * (r34 * d4); h1 = y1 * (r34 * d3);
                     } else {
-                        float d1, d2, d3, d4;
-                        upk(add2(pk(ex2_approx(fminf(z0, 60.0f)), ex2_approx(fminf(z1, 60.0f))), one2), d1, d2);
-                        upk(add2(pk(ex2_approx(fminf(y0, 60.0f)), ex2_approx(fminf(y1, 60.0f))), one2), d3, d4);
+                        const float d1 = 1.0f + ex2_approx(fminf(z0, 60.0f)), d2 = 1.0f + ex2_approx(fminf(z1, 60.0f));
+                        const float d3 = 1.0f + ex2_approx(fminf(y0, 60.0f)), d4 = 1.0f + ex2_approx(fminf(y1, 60.0f));
                         const float r12 = rcp_approx(d1 * d2), r34 = rcp_approx(d3 * d4);
-                        sg12 = pk(r12 * d2, r12 * d1); sg34 = pk(r34 * d4, r34 * d3);
+                        s0 = z0 * (r12 * d2); s1 = z1 * (r12 * d1);
+                        h0 = y0 * (r34 * d4); h1 = y1 * (r34 * d3);
                     }
-                    const f32x2 sv = mul2(pk(z0, z1), sg12), hv = mul2(pk(y0, y1), sg34);   // z * sigmoid; the -ln 2 lives in the head weights
-                    psd2[j] = fma2(sv, hw.x, psd2[j]);
-                    pr2[j] = fma2(hv, hw.y, pr2[j]); pg2[j] = fma2(hv, hw.z, pg2[j]); pb2[j] = fma2(hv, hw.w, pb2[j]);
+                    psd[j] = fmaf(s0, hw0.x, psd[j]);
+                    psd[j] = fmaf(s1, hw1.x, psd[j]);
+                    pr[j] = fmaf(h0, hw0.y, pr[j]); pg[j] = fmaf(h0, hw0.z, pg[j]); pb[j] = fmaf(h0, hw0.w, pb[j]);
+                    pr[j] = fmaf(h1, hw1.y, pr[j]); pg[j] = fmaf(h1, hw1.z, pg[j]); pb[j] = fmaf(h1, hw1.w, pb[j]);
                 }
-            }
-            float psd[4], pr[4], pg[4], pb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float a, b;
-                upk(psd2[j], a, b); psd[j] = a + b;
-                upk(pr2[j], a, b); pr[j] = a + b;
-                upk(pg2[j], a, b); pg[j] = a + b;
-                upk(pb2[j], a, b); pb[j] = a + b;
             }
             // reduce over the 4 lanes of the quad (columns), then lane 4g+j keeps row g+8j and ships it to the owning lane
 #pragma unroll
@@ -387,10 +374,10 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
     }
 }
 
-template <int MINB, bool EDF>
+template <int MINB, bool EDF, int ABL>
 static int p3_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream) {
     const size_t smem = EDF ? sizeof(SmemP3) : offsetof(SmemP3, edf);
-    auto kern = k_render_p3<MINB, EDF>;
+    auto kern = k_render_p3<MINB, EDF, ABL>;
     static DeviceOnce attr_set;
     if (attr_set.first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -410,19 +397,24 @@ static int p3_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist
     return 0;
 }
 
-// SSDNERF_P3_MODE = "edf3" (exp table, 3 CTAs / SM) | "noedf3" | "noedf4" (no table, <= 128 registers, 4 CTAs / SM) | "noedf5"; A/B runs
+// SSDNERF_P3_MODE = "noedf3" (default: no table, 3 CTAs / SM) | "noedf4" (<= 128 registers, 4 CTAs / SM) | "edf3" (exp table); A/B runs
 int render_p3_launch(const RenderParams& p, int emulate_schedule, uint32_t* hist, int sms, cudaStream_t stream) {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("SSDNERF_P3_MODE");
-        mode = 2;
-        if (e) mode = !strcmp(e, "edf3") ? 0 : !strcmp(e, "noedf3") ? 1 : !strcmp(e, "noedf4") ? 2 : !strcmp(e, "noedf5") ? 3 : 2;
+        mode = 1;      // measured on B200 (dense / sphere workloads, G samples/s): noedf3 9.70 / 4.40, noedf4 9.48 / 4.55, edf3 9.20 / 4.20, k_render_p2 9.42 / 4.22
+        if (e) mode = !strcmp(e, "edf3") ? 0 : !strcmp(e, "noedf3") ? 1 : !strcmp(e, "noedf4") ? 2 : 1;
     }
+    static int abl = -1;
+    if (abl < 0) { const char* e = getenv("SSDNERF_P3_ABLATE"); abl = e ? atoi(e) : 0; }
+    if (abl == 1) return p3_launch<3, false, 1>(p, emulate_schedule, hist, sms, stream);
+    if (abl == 2) return p3_launch<3, false, 2>(p, emulate_schedule, hist, sms, stream);
+    if (abl == 3) return p3_launch<3, false, 3>(p, emulate_schedule, hist, sms, stream);
+    if (abl == 4) return p3_launch<3, false, 4>(p, emulate_schedule, hist, sms, stream);
     switch (mode) {
-        case 0: return p3_launch<3, true>(p, emulate_schedule, hist, sms, stream);
-        case 1: return p3_launch<3, false>(p, emulate_schedule, hist, sms, stream);
-        case 3: return p3_launch<5, false>(p, emulate_schedule, hist, sms, stream);
-        default: return p3_launch<4, false>(p, emulate_schedule, hist, sms, stream);
+        case 0: return p3_launch<3, true, 0>(p, emulate_schedule, hist, sms, stream);
+        case 2: return p3_launch<4, false, 0>(p, emulate_schedule, hist, sms, stream);
+        default: return p3_launch<3, false, 0>(p, emulate_schedule, hist, sms, stream);
     }
 }
 

@@ -58,20 +58,27 @@ def test_config1_explicit_rays(cuda, variant, grid):
     out = _run_gpu(variant, vid, params, code, bf, poses, intr, res, cuda, max_steps, True, max(cap, 1))
     counts_ref = np.array([len(t) for t in ref['trace']], np.int32)
     counts = out['num_samples'][0]
+    tr = out['trace'][0]
     if variant[0] != 'S':
         assert np.array_equal(counts, counts_ref)
-    else:   # early termination depends on sigma; fp16 MLP may stop one sample apart on a handful of rays
-        assert (counts != counts_ref).mean() < 5e-3
-    same = counts == counts_ref
-    tr = out['trace'][0]
-    for i in np.nonzero(same)[0]:
-        assert list(tr[i, :counts[i]]) == ref['trace'][i], f'ray {i}'
+    else:
+        # The occupancy-hit SEQUENCE is integer work and bit-exact for every ray.  Where a ray STOPS depends on a float comparison
+        # (T < 1e-4 on the accumulated transmittance): the fp16 MLP can cross that threshold one sample earlier or later than the fp32
+        # oracle on a handful of rays -- then one trace is a prefix of the other and the extra sample carries a weight < 1e-4.
+        differ = np.nonzero(counts != counts_ref)[0]
+        assert len(differ) <= max(2, int(2e-3 * len(counts))), len(differ)
+        assert np.abs(counts - counts_ref).max() <= 1
+    for i in range(len(counts)):
+        n = min(counts[i], counts_ref[i])
+        assert list(tr[i, :n]) == ref['trace'][i][:n], f'ray {i}'
     tol = TOL_S if variant[0] == 'S' else TOL_P
-    np.testing.assert_allclose(out['image'][0][same], ref['image'][same], **tol)
-    np.testing.assert_allclose(out['weights_sum'][0][same], ref['weights_sum'][same], **tol)
-    np.testing.assert_allclose(out['depth'][0][same], ref['depth'][same], rtol=tol['rtol'], atol=tol['atol'] * 4)
+    err = np.abs(out['image'][0] - ref['image'])
+    print(f'{variant}/{grid}: image max abs err {err.max():.2e} mean {err.mean():.2e}; rays with a different sample count: {(counts != counts_ref).sum()}')
+    np.testing.assert_allclose(out['image'][0], ref['image'], **tol)                 # every ray, including the ones that stopped one sample apart
+    np.testing.assert_allclose(out['weights_sum'][0], ref['weights_sum'], **tol)
+    np.testing.assert_allclose(out['depth'][0], ref['depth'], rtol=tol['rtol'], atol=tol['atol'] * 4)
     blend = ref['image'] + 1.0 * (1 - ref['weights_sum'][:, None])
-    np.testing.assert_allclose(out['rgb'][0][same], blend[same], **tol)
+    np.testing.assert_allclose(out['rgb'][0], blend, **tol)
 
 
 @pytest.mark.parametrize('variant', ['P', 'S'])
