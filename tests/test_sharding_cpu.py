@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ssdnerf_b200.sharding import gather_scene_outputs, scene_indices
+from ssdnerf_b200.sharding import broadcast_scene, gather_scene_outputs, gather_views, max_views_per_rank, scene_indices, view_range
 
 
 def _free_port():
@@ -23,7 +23,15 @@ def _worker(rank, world, port, num_scenes, q):
     # max-over-ranks timing reduction used by bench.py
     t = torch.tensor([10.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    q.put((rank, idx, full[:, 0, 0].tolist(), float(t)))
+    # view sharding (strong scaling): rank 0 owns the scene, every rank renders its view range, images are gathered in view order
+    code = torch.arange(6, dtype=torch.float32).reshape(1, 6) * (1 if rank == 0 else -1)
+    bits = torch.full((1, 4), 7 if rank == 0 else 0, dtype=torch.uint8)
+    broadcast_scene(code, bits)
+    V = 7
+    lo, hi = view_range(V)
+    local = torch.arange(lo, hi, dtype=torch.uint8)[:, None].repeat(1, 3) + bits[0, 0]
+    views = gather_views(local, V)
+    q.put((rank, idx, full[:, 0, 0].tolist(), float(t), code[0].tolist(), views[:, 0].tolist()))
     dist.destroy_process_group()
 
 
@@ -44,6 +52,14 @@ def test_world_size_2_gloo_gather():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, idx, full, tmax in res:
+    for rank, idx, full, tmax, code, views in res:
         assert full == [0.0, 1.0, 2.0, 3.0, 4.0] and tmax == 11.0
         assert idx == list(range(rank, 5, 2))
+        assert code == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and views == [7 + v for v in range(7)]
+
+
+def test_view_ranges_partition_the_views():
+    for V, W in ((251, 8), (251, 1), (7, 2), (3, 8)):
+        r = [view_range(V, k, W) for k in range(W)]
+        assert r[0][0] == 0 and r[-1][1] == V and all(r[k][1] == r[k + 1][0] for k in range(W - 1))
+        assert max_views_per_rank(V, W) - min(hi - lo for lo, hi in r) <= 1
