@@ -221,7 +221,12 @@ __global__ void __launch_bounds__(kP3Threads, MINB) k_render_p3(RenderParams p, 
                 if (ABL == 4) { x = fmaf(t, r.dx, r.ox); y = fmaf(t, r.dy, r.oy); z = fmaf(t, r.dz, r.oz); dt = c.dt_min; vi = 0; has = true; }
                 else has = probe(c, r, grid, t, x, y, z, dt, vi);
             }
-            if (!__any_sync(0xffffffffu, has)) break;
+            const unsigned has_mask = __ballot_sync(0xffffffffu, has);
+            if (!has_mask) break;
+            if (p.prof && lane == 0) {       // debug instrumentation (NULL in production): lane utilisation of the decode iterations
+                atomicAdd(p.prof, 1ULL);
+                atomicAdd(p.prof + 1, (unsigned long long)__popc(has_mask));
+            }
 
             // ---- phase 2: bilinear features of this lane's sample -> split fp16 row of the warp's A tile
             if (has) {

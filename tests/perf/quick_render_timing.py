@@ -32,6 +32,11 @@ for emu in (1,):
     ms = e0.elapsed_time(e1) / 5
     ns = out['num_samples'].sum().item()
     rays = B * V * res * res
+    if variant == 'P_MMA2':
+        prof = torch.zeros(8, dtype=torch.int64, device=dev)
+        R.render_fwd(vid, planes, (128, 128), bf, blob, poses=poses, intrinsics=intr, img_hw=(res, res), emulate_schedule=False, debug_phase_cycles=prof)
+        pc = prof.cpu().numpy()
+        print('decode iterations', int(pc[0]), 'samples', int(pc[1]), 'lane utilisation %.3f' % (pc[1] / (32.0 * max(pc[0], 1))))
     if variant == 'P_TC':
         prof = torch.zeros(8, dtype=torch.int64, device=dev)
         R.render_fwd(vid, planes, (128, 128), bf, blob, poses=poses, intrinsics=intr, img_hw=(res, res), emulate_schedule=False, debug_phase_cycles=prof)

@@ -93,5 +93,5 @@ def up_forward_cuda(sd, spec, x, t):
 
 
 if __name__ == '__main__':
-    res = dict(render=[time_render(V) for V in (1, 8, 32)], unet=[time_unet(16, False), time_unet(16, True)])
+    res = dict(render=[time_render(V) for V in (1, 8, 32, 128, 251)], unet=[time_unet(16, False), time_unet(16, True)])
     print(json.dumps(res, indent=1))

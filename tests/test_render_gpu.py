@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 
 # fp32 CUDA-core MLP (variant P): only round-off / fast-intrinsic differences vs the fp32 oracle
 TOL_P = dict(rtol=2e-4, atol=2e-5)
-# fp16 tensor-core MLP + fp16 planes (variant S): BASELINE.json north_star "1e-3 relative fp16 tolerance"
-# on rendered RGB, measured relative to the image range [0, 1]
-TOL_S = dict(rtol=0, atol=4e-3)
+# fp16 tensor-core MLP + fp16 planes (variant S): BASELINE.json north_star "1e-3 relative fp16 tolerance" on rendered RGB, taken on the
+# image range [0, 1].  Measured on the B200: max abs error 8.7e-5 (dense grid) / 5.1e-5 (sphere); the bar is half the stated tolerance.
+TOL_S = dict(rtol=0, atol=5e-4)
 
 
 def _bitfields():
