@@ -262,6 +262,11 @@ typedef struct ssdnerf_gemm_args {
     float* qstats; uint32_t stats_hw;
     void* debug_cycles;      /* optional uint64[8] device counters (pipeline wait cycles per role, summed over CTAs); NULL in production */
     uint32_t algo;           /* 0 = auto, 1 = generic tile kernel, 2 = row-pair 3x3 convolution (128-pixel rows, 128 output channels) */
+    /* generalised K-slabs: taps in [1, 9] with tap_offsets[2t], [2t+1] = shift of slab t in (d1, d2) (NULL: the 3x3 / 1x1 defaults) --
+     * e.g. the four 2x2-tap phase convolutions a nearest-x2 upsample + 3x3 convolution decomposes into;
+     * a_stride 2 = stride-2 convolution: (d1, d2) are output extents, a1 / a2 describe the (2 d1 x 2 d2) input read at every 2nd pixel */
+    const int8_t* tap_offsets;   /* HOST pointer, 2 * taps entries, or NULL */
+    uint32_t a_stride;           /* 0 / 1: dense; 2: stride-2 convolution */
 } ssdnerf_gemm_args;
 SSDNERF_API int ssdnerf_gemm_f16(const ssdnerf_gemm_args* args, void* stream);
 

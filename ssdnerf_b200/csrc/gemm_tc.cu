@@ -35,7 +35,9 @@ struct GemmParams {
     uint32_t d1, d2, d3;        // problem extents
     uint32_t T1, T2, T3;        // tiles along d1, d2, d3
     uint32_t tiles_n;
-    uint32_t taps;              // 1 or 9
+    uint32_t taps;              // 1 .. 9 K-slabs; slab t reads A shifted by (tap_ox[t], tap_oy[t]) in (d1, d2)
+    int8_t tap_ox[9], tap_oy[9];
+    uint32_t a_stride;          // 1, or 2: stride-2 convolution (output tile coordinates x 2 in d1 / d2, A tensor map traverses every 2nd element)
     uint32_t kc1, kc2;          // 64-wide K chunks taken from A1 / A2 per tap
     uint32_t n_valid;           // output columns
     uint32_t b_batched;         // B coords (c2, c3) = (t2, t3) instead of (tap, 0)
@@ -133,13 +135,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUt
                 const uint32_t m_tile = (tile % sup_m) * CL + crank, n_tile = tile / sup_m;     // m_tile may be >= tiles_m in the last
                 const uint32_t t1 = m_tile % p.T1, t2 = (m_tile / p.T1) % p.T2, t3 = m_tile / (p.T1 * p.T2);   // super-tile: loads zero-fill
                 for (uint32_t tap = 0; tap < p.taps; ++tap) {
-                    const int ox = (p.taps == 9) ? (int)(tap % 3) - 1 : 0;
-                    const int oy = (p.taps == 9) ? (int)(tap / 3) - 1 : 0;
+                    const int ox = p.tap_ox[tap], oy = p.tap_oy[tap];
                     for (uint32_t j = 0; j < p.kc1 + p.kc2; ++j) {
                         if (p.prof) { const long long c = clock64(); mbar_wait(&empty[stage], phase ^ 1); pw += clock64() - c; }
                         else mbar_wait(&empty[stage], phase ^ 1);
                         const bool first = j < p.kc1;
-                        const int ak = (int)((first ? j : j - p.kc1) * kBK), a1 = (int)(t1 * p.b1) + ox, a2 = (int)(t2 * p.b2) + oy, a3 = (int)(t3 * p.b3);
+                        const int ak = (int)((first ? j : j - p.kc1) * kBK), a1 = (int)(t1 * p.b1 * p.a_stride) + ox, a2 = (int)(t2 * p.b2 * p.a_stride) + oy, a3 = (int)(t3 * p.b3);
                         if (CL == 1) {
                             mbar_expect_tx_w(&full[stage], Cfg::kTxBytes);
                             tma_load_4d_w(sA + stage * kABytes, first ? &mapA1 : &mapA2, &full[stage], ak, a1, a2, a3);
@@ -415,15 +416,16 @@ static PFN_encodeTiled get_encode() {
 
 // fp16 4-D map: dims {K, e1, e2, e3}, byte strides {s1, s2, s3} (K contiguous), box {64, x1, x2, x3}, SWIZZLE_128B
 static int make_map_4d(CUtensorMap* m, const void* base, uint64_t K, uint64_t e1, uint64_t e2, uint64_t e3, uint64_t s1, uint64_t s2,
-                       uint64_t s3, uint32_t x1, uint32_t x2, uint32_t x3) {
+                       uint64_t s3, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t trav = 1) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return set_error_msg(SSDNERF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     if (((uintptr_t)base & 15u) || (s1 & 15u) || (s2 & 15u) || (s3 & 15u))
         return set_error_msg(SSDNERF_ERR_ARG, "gemm: TMA operands need 16-byte aligned base and strides");
     cuuint64_t dims[4] = {K, e1, e2, e3};
     cuuint64_t strides[3] = {s1, s2, s3};
-    cuuint32_t box[4] = {64, x1, x2, x3};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // trav = 2 (stride-2 convolution): the box spans 2*x1 by 2*x2 source elements and every second one is delivered
+    cuuint32_t box[4] = {64, x1 * trav, x2 * trav, x3};
+    cuuint32_t estr[4] = {1, trav, trav, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -492,14 +494,18 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     if (!a || !a->a1 || !a->b || !a->out) return set_error_msg(SSDNERF_ERR_ARG, "gemm: a1, b and out are required");
     if (a->k1 == 0 || a->k1 % 64 || a->k2 % 64) return set_error_msg(SSDNERF_ERR_ARG, "gemm: K extents must be multiples of 64");
     if (a->b1 * a->b2 * a->b3 != 128) return set_error_msg(SSDNERF_ERR_ARG, "gemm: b1*b2*b3 must be 128");
-    if (a->taps != 1 && a->taps != 9) return set_error_msg(SSDNERF_ERR_ARG, "gemm: taps must be 1 or 9");
-    if (a->taps == 9 && a->b_batched) return set_error_msg(SSDNERF_ERR_ARG, "gemm: conv taps and batched B are exclusive");
+    if (a->taps < 1 || a->taps > 9) return set_error_msg(SSDNERF_ERR_ARG, "gemm: taps must be in [1, 9]");
+    if (a->taps != 1 && a->taps != 9 && !a->tap_offsets) return set_error_msg(SSDNERF_ERR_ARG, "gemm: taps other than 1 / 9 need tap_offsets");
+    if (a->taps > 1 && a->b_batched) return set_error_msg(SSDNERF_ERR_ARG, "gemm: conv taps and batched B are exclusive");
+    if (a->a_stride > 2) return set_error_msg(SSDNERF_ERR_ARG, "gemm: a_stride must be 0 / 1 / 2");
+    const uint32_t a_stride = a->a_stride == 2 ? 2u : 1u;
+    if (a_stride == 2 && (a->b1 * 2 > 256 || a->b2 * 2 > 256)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: stride-2 boxes exceed the 256-element TMA limit");
     if (a->n == 0 || a->d1 == 0 || a->d2 == 0 || a->d3 == 0) return 0;
     int dev = 0, sms = 0;
     SSDNERF_CUDA_OK(cudaGetDevice(&dev));
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // 3x3 convolution over 128-pixel rows with 128 output channels (the UNet's 128 x 128 level): row-pair kernel with halo reuse
-    if (a->algo != 1 && a->taps == 9 && a->d1 == 128 && a->b1 == 128 && a->b2 == 1 && a->b3 == 1 && a->n == 128 && !a->out_f32 && !a->b_batched &&
+    if (a->algo != 1 && a->taps == 9 && !a->tap_offsets && a_stride == 1 && a->d1 == 128 && a->b1 == 128 && a->b2 == 1 && a->b3 == 1 && a->n == 128 && !a->out_f32 && !a->b_batched &&
         (a->d2 % 2) == 0 && a->alpha == 1.0f && (a->bn == 0 || a->bn == 128) && a->cluster <= 1 && a->so1 == 128 && a->so2 == 128 * 128 &&
         a->so3 == (long long)a->d2 * 128 * 128 && (!a->qstats || a->stats_hw == 0) && (a->n_rows_b == 0 || a->n_rows_b >= 128))
         return ssdnerf::conv_row2_launch(a, sms, stream);
@@ -526,19 +532,28 @@ extern "C" int ssdnerf_gemm_f16(const ssdnerf_gemm_args* a, void* stream_) {
     p.b1 = a->b1; p.b2 = a->b2; p.b3 = a->b3; p.d1 = a->d1; p.d2 = a->d2; p.d3 = a->d3;
     p.T1 = div_up(a->d1, a->b1); p.T2 = div_up(a->d2, a->b2); p.T3 = div_up(a->d3, a->b3);
     p.tiles_n = div_up(a->n, (uint32_t)bn);
+    p.a_stride = a_stride;
+    for (uint32_t t = 0; t < 9; ++t) {
+        if (a->tap_offsets) { p.tap_ox[t] = a->tap_offsets[2 * t]; p.tap_oy[t] = a->tap_offsets[2 * t + 1]; }
+        else if (a->taps == 9) { p.tap_ox[t] = (int8_t)((int)(t % 3) - 1); p.tap_oy[t] = (int8_t)((int)(t / 3) - 1); }
+        else { p.tap_ox[t] = 0; p.tap_oy[t] = 0; }
+    }
     p.taps = a->taps; p.kc1 = a->k1 / 64; p.kc2 = a->a2 ? a->k2 / 64 : 0; p.n_valid = a->n; p.b_batched = a->b_batched;
     p.alpha = a->alpha; p.bias_n = a->bias_n; p.residual = (const __half*)a->residual; p.out = a->out; p.out_f32 = a->out_f32;
     p.so1 = a->so1; p.so2 = a->so2; p.so3 = a->so3;
     p.qstats = a->qstats; p.stats_hw = a->stats_hw; p.prof = (unsigned long long*)a->debug_cycles;
     if (a->bias_n && a->n > (uint32_t)kMaxBiasN) return set_error_msg(SSDNERF_ERR_ARG, "gemm: bias vectors longer than 2048 are not supported");
     if (a->qstats && (a->n % 4)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: quad statistics need n % 4 == 0");
+    if (a->qstats && !a->stats_hw && a->b3 > 2) return set_error_msg(SSDNERF_ERR_ARG, "gemm: fused quad statistics cover at most 2 images per 128-row tile (b3 <= 2)");
     if (a->qstats && a->stats_hw && (a->stats_hw % 64)) return set_error_msg(SSDNERF_ERR_ARG, "gemm: stats_hw must be a multiple of 64");
     const uint64_t ktot = (uint64_t)a->k1 + (a->a2 ? a->k2 : 0);
 
     CUtensorMap mA1, mA2, mB;
-    if (int e = make_map_4d(&mA1, a->a1, a->k1, a->d1, a->d2, a->d3, a->a1_strides[0], a->a1_strides[1], a->a1_strides[2], a->b1, a->b2, a->b3)) return e;
+    // stride 2: (d1, d2) are OUTPUT extents; the tensor map covers the input image (2 d1 x 2 d2) and is traversed with element stride 2
+    const uint64_t e1 = (uint64_t)a->d1 * a_stride, e2 = (uint64_t)a->d2 * a_stride;
+    if (int e = make_map_4d(&mA1, a->a1, a->k1, e1, e2, a->d3, a->a1_strides[0], a->a1_strides[1], a->a1_strides[2], a->b1, a->b2, a->b3, a_stride)) return e;
     if (a->a2) {
-        if (int e = make_map_4d(&mA2, a->a2, a->k2, a->d1, a->d2, a->d3, a->a2_strides[0], a->a2_strides[1], a->a2_strides[2], a->b1, a->b2, a->b3)) return e;
+        if (int e = make_map_4d(&mA2, a->a2, a->k2, e1, e2, a->d3, a->a2_strides[0], a->a2_strides[1], a->a2_strides[2], a->b1, a->b2, a->b3, a_stride)) return e;
     } else {
         mA2 = mA1;
     }

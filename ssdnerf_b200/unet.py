@@ -281,10 +281,9 @@ class UNetEngine:
             if isinstance(p, _ResBlockParams): return res(p)
             if isinstance(p, _AttnParams): return attn(p)
             if isinstance(p, _DownParams):
-                w = p.downsample.weight.detach().permute(0, 2, 3, 1).reshape(p.c, 9 * p.c)      # K index = tap*C + c
-                return ('down', dict(c=p.c, w=U.pack_linear_weight(w).to(dev), b=f32(p.downsample.bias)))
+                return ('down', dict(c=p.c, w=U.pack_conv_weight(p.downsample.weight).to(dev), b=f32(p.downsample.bias)))
             if isinstance(p, _UpParams):
-                return ('up', dict(c=p.c, w=U.pack_conv_weight(p.conv.weight).to(dev), b=f32(p.conv.bias)))
+                return ('up', dict(c=p.c, w=U.pack_upconv_weight(p.conv.weight).to(dev), b=f32(p.conv.bias)))
             raise TypeError(type(p))
 
         conv_in = m.in_blocks[0][0]
@@ -431,12 +430,9 @@ class UNetEngine:
     def _down(self, d, x, tag):
         x, _ = x
         B, H, W, c = x.shape
-        col = self._buf(('col', H, c), (B, H // 2, W // 2, 9 * c))
-        N.check(N.lib().ssdnerf_im2col_s2(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(col), N.stream_ptr()))
-        M = B * (H // 2) * (W // 2)
         qo = self._q(('down_out', tag), c)
-        out = U.linear_f16(col.view(M, 9 * c), d['w'], bias=d['b'], n=c, out=self._buf(('down_out', tag), (M, c)), qstats=qo,
-                           stats_hw=(H // 2) * (W // 2)).view(B, H // 2, W // 2, c)
+        # stride-2 convolution straight from x: TMA boxes traverse every second pixel (no im2col buffer)
+        out = U.conv3x3_s2_f16(x, d['w'], c, bias=d['b'], out=self._buf(('down_out', tag), (B, H // 2, W // 2, c)), qstats=qo)
         if self.saving:
             self.tape.append(dict(kind='down', d=d, x=x, out=out, tag=tag))
         return out, qo
@@ -444,10 +440,9 @@ class UNetEngine:
     def _up(self, d, x, tag):
         x, _ = x
         B, H, W, c = x.shape
-        up = self._buf(('upx', H, c), (B, 2 * H, 2 * W, c))
-        N.check(N.lib().ssdnerf_upsample2x(N.ptr(x), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(up), N.stream_ptr()))
         qo = self._q(('up_out', tag), c)
-        out = U.conv3x3_f16(up, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)), qstats=qo)
+        # nearest x2 + conv3x3 as four 2x2-tap phase convolutions of the low-resolution tensor (no upsampled buffer, 4/9 of the flops)
+        out = U.upconv3x3_f16(x, d['w'], c, bias=d['b'], out=self._buf(('up_out', tag), (B, 2 * H, 2 * W, c)), qstats=qo)
         if self.saving:
             self.tape.append(dict(kind='up', d=d, x=x, out=out, tag=tag))
         return out, qo

@@ -24,6 +24,7 @@ class GemmArgs(ctypes.Structure):
         ('bn', N.c_u32), ('cluster', N.c_u32), ('alpha', N.c_f32), ('bias_n', N.c_void_p), ('residual', N.c_void_p),
         ('out', N.c_void_p), ('out_f32', N.c_u32), ('so1', c_ll), ('so2', c_ll), ('so3', c_ll),
         ('qstats', N.c_void_p), ('stats_hw', N.c_u32), ('debug_cycles', N.c_void_p), ('algo', N.c_u32),
+        ('tap_offsets', N.c_void_p), ('a_stride', N.c_u32),
     ]
 
 
@@ -131,6 +132,89 @@ def conv3x3_f16(x, wp, cout, bias=None, x2=None, residual=None, out=None, out_f3
     if qstats is not None:
         g.qstats, g.stats_hw = qstats.data_ptr(), 0
     _launch(g)
+    return out
+
+
+def conv3x3_s2_f16(x, wp, cout, bias=None, out=None, qstats=None):
+    """3x3 stride-2 pad-1 convolution (mmgen DenoisingDownsample) over NHWC fp16 x [B,H,W,C] -> [B,H/2,W/2,cout] WITHOUT an im2col
+    buffer: the same implicit GEMM as the stride-1 convolution, its TMA boxes traversing every second input pixel (a_stride = 2)."""
+    N.require_cuda(x, wp)
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and H % 2 == 0 and W % 2 == 0 and wp.shape[-1] == C and C % 64 == 0
+    Ho, Wo = H // 2, W // 2
+    if out is None:
+        out = torch.empty(B, Ho, Wo, cout, dtype=torch.float16, device=x.device)
+    bw, bh, nb = _conv_boxes(Ho, Wo)
+    g = GemmArgs()
+    g.a1, g.k1 = x.data_ptr(), C
+    g.a1_strides = (c_u64 * 3)(C * 2, W * C * 2, H * W * C * 2)
+    g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = Wo, Ho, B, bw, bh, nb
+    g.taps, g.a_stride = 9, 2
+    rows = wp.shape[-2]
+    g.b, g.n, g.n_rows_b, g.bx2, g.bx3 = wp.data_ptr(), cout, rows, 9, 1
+    g.b_strides = (c_u64 * 3)(C * 2, rows * C * 2, 9 * rows * C * 2)
+    g.bn, g.alpha, g.algo = 0, 1.0, 1
+    g.bias_n = bias.data_ptr() if bias is not None else None
+    g.out, g.out_f32 = out.data_ptr(), int(out.dtype == torch.float32)
+    g.so1, g.so2, g.so3 = cout, Wo * cout, Ho * Wo * cout
+    if qstats is not None:
+        g.qstats, g.stats_hw = qstats.data_ptr(), 0
+    _launch(g)
+    return out
+
+
+_UP_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}     # output parity -> ((source offset, merged kernel rows), ...)
+
+
+def pack_upconv_weight(w):
+    """nearest-x2 upsample followed by conv3x3 == four 2x2-tap convolutions of the LOW-resolution image, one per output parity
+    (py, px): kernel rows / columns that read the same source pixel are summed.  w [Cout, Cin, 3, 3] -> fp16 [4 phases][4 taps][Cout_pad][Cin]
+    (phase = py*2 + px, tap = iy*2 + ix) -- 16 tap-GEMMs at a quarter of the pixels = 4/9 of the flops, and no upsampled tensor."""
+    w = w.detach().float()
+    phases = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for _, kys in _UP_ROWS[py]:
+                for _, kxs in _UP_ROWS[px]:
+                    taps.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))
+            phases.append(torch.stack(taps))                     # [4, Cout, Cin]
+    wp = torch.stack(phases).half()                              # [4, 4, Cout, Cin]
+    assert wp.shape[-1] % 64 == 0
+    return _pad_rows(wp).contiguous()
+
+
+def upconv3x3_f16(x, wps, cout, bias=None, out=None, qstats=None):
+    """conv3x3(nearest_x2(x)) (mmgen DenoisingUpsample) from the low-resolution x [B,H,W,C] -> [B,2H,2W,cout]; wps = pack_upconv_weight."""
+    N.require_cuda(x, wps)
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and wps.shape[-1] == C
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, cout, dtype=torch.float16, device=x.device)
+    bw, bh, nb = _conv_boxes(H, W)
+    rows = wps.shape[-2]
+    esz = out.element_size()
+    for py in (0, 1):
+        for px in (0, 1):
+            offs = (ctypes.c_int8 * 8)(*[v for oy, _ in _UP_ROWS[py] for ox, _ in _UP_ROWS[px] for v in (ox, oy)])
+            g = GemmArgs()
+            g.a1, g.k1 = x.data_ptr(), C
+            g.a1_strides = (c_u64 * 3)(C * 2, W * C * 2, H * W * C * 2)
+            g.d1, g.d2, g.d3, g.b1, g.b2, g.b3 = W, H, B, bw, bh, nb
+            g.taps, g.a_stride = 4, 1
+            g.tap_offsets = ctypes.cast(offs, ctypes.c_void_p)
+            ph = py * 2 + px
+            g.b = wps.data_ptr() + ph * 4 * rows * C * 2
+            g.n, g.n_rows_b, g.bx2, g.bx3 = cout, rows, 4, 1
+            g.b_strides = (c_u64 * 3)(C * 2, rows * C * 2, 4 * rows * C * 2)
+            g.bn, g.alpha, g.algo = 0, 1.0, 1
+            g.bias_n = bias.data_ptr() if bias is not None else None
+            g.out = out.data_ptr() + (py * 2 * W + px) * cout * esz
+            g.out_f32 = int(out.dtype == torch.float32)
+            g.so1, g.so2, g.so3 = 2 * cout, 2 * (2 * W) * cout, 4 * H * W * cout
+            if qstats is not None:
+                g.qstats, g.stats_hw = qstats.data_ptr(), 0
+            _launch(g)
     return out
 
 

@@ -165,3 +165,34 @@ def test_fused_groupnorm_silu_conv(cuda, B, H, C1, C2, use_ss):
         xn = xn * (1 + ss[:, 64:64 + C, None, None]) + ss[:, 64 + C:64 + 2 * C, None, None]
     ref = torch.nn.functional.conv2d(torch.nn.functional.silu(xn), w.half().float().to(cuda), bias, padding=1).permute(0, 2, 3, 1) + res.float()
     _check(out, ref, tol=5e-3)
+
+
+@pytest.mark.parametrize('B,H,C,Cout', [(2, 16, 128, 128), (3, 16, 512, 512), (1, 128, 128, 128), (2, 64, 256, 256), (5, 32, 256, 256)])
+def test_stride2_conv_and_upsample_conv_without_intermediate_buffers(cuda, B, H, C, Cout):
+    """DenoisingDownsample (conv3x3 stride 2) straight from the input through stride-2 TMA boxes, and DenoisingUpsample (nearest x2 + conv3x3)
+    as four 2x2-tap phase convolutions of the low-resolution tensor, vs F.conv2d on the same fp16 operands; fused quad statistics too."""
+    import torch.nn.functional as F
+    from ssdnerf_b200 import unet_ops as U
+    g = torch.Generator().manual_seed(H + C)
+    x = torch.randn(B, H, H, C, generator=g).half().to(cuda)
+    w = torch.randn(Cout, C, 3, 3, generator=g) * 0.05
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    xr = x.float().permute(0, 3, 1, 2)
+    wr = w.half().float().to(cuda)
+    # stride 2
+    q = torch.zeros(B, Cout // 4, 2, device=cuda)
+    y = U.conv3x3_s2_f16(x, U.pack_conv_weight(w).to(cuda), Cout, bias=bias, qstats=q)
+    ref = F.conv2d(xr, wr, bias, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert (y.float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 2e-3
+    rq = ref.reshape(B, -1, Cout // 4, 4)
+    torch.testing.assert_close(q, torch.stack([rq.sum(dim=(1, 3)), (rq * rq).sum(dim=(1, 3))], dim=-1), rtol=2e-3, atol=2e-2)
+    # nearest x2 + conv: the merged-tap weights are rounded to fp16 once (w1 + w2 -> fp16), so compare against the fp32-weight reference
+    q2 = torch.zeros(B, Cout // 4, 2, device=cuda)
+    y2 = U.upconv3x3_f16(x, U.pack_upconv_weight(w).to(cuda), Cout, bias=bias, qstats=q2)
+    ref2 = F.conv2d(F.interpolate(xr, scale_factor=2, mode='nearest'), w.to(cuda), bias, padding=1).permute(0, 2, 3, 1)
+    assert y2.shape == ref2.shape
+    assert (y2.float() - ref2).abs().max().item() < 3e-3 * ref2.abs().max().item() + 3e-3
+    assert float((y2.float() - ref2).norm() / ref2.norm()) < 1e-3
+    rq2 = ref2.reshape(B, -1, Cout // 4, 4)
+    torch.testing.assert_close(q2, torch.stack([rq2.sum(dim=(1, 3)), (rq2 * rq2).sum(dim=(1, 3))], dim=-1), rtol=3e-3, atol=5e-2)
