@@ -158,6 +158,33 @@ def module_requires_grad(module, requires_grad=True):
             p.requires_grad_(r)
 
 
+def extract_fields(decoder, code_single, resolution=256, margin=0.1):
+    """density sigma on a resolution^3 lattice over [aabb_min - margin, aabb_max + margin] (lib/core/utils/nerf_utils.py:64-81 + the
+    query of :98-106): ONE native point-decode launch instead of the reference's 8 chunked host round trips; points outside the AABB
+    read 0.  Returns a float32 CUDA tensor [R, R, R] indexed [x, y, z]."""
+    dev = code_single.device
+    lo, hi = decoder.aabb[:3].to(dev) - margin, decoder.aabb[3:].to(dev) + margin
+    axes = [torch.linspace(float(lo[i]), float(hi[i]), resolution, device=dev) for i in range(3)]
+    pts = torch.stack(torch.meshgrid(*axes, indexing='ij'), dim=-1).reshape(1, -1, 3)
+    sigma, _ = decoder.point_density_decode(pts, code_single[None])
+    outside = ((pts[0] < decoder.aabb[:3].to(dev)) | (pts[0] > decoder.aabb[3:].to(dev))).any(dim=-1)
+    return sigma.masked_fill(outside, 0).reshape(resolution, resolution, resolution)
+
+
+def extract_geometry(decoder, code_single, resolution=256, threshold=10):
+    """nerf_utils.py:84-112: marching cubes (PyMCubes, as in the reference) over `extract_fields`"""
+    try:
+        import mcubes
+    except ImportError as e:
+        raise ImportError('extract_geometry needs PyMCubes (`mcubes`), like the reference') from e
+    with torch.no_grad():
+        u = extract_fields(decoder, code_single, resolution).cpu().numpy()
+    vertices, triangles = mcubes.marching_cubes(u, threshold)
+    lo = (decoder.aabb[:3] - 0.1).cpu().numpy()
+    hi = (decoder.aabb[3:] + 0.1).cpu().numpy()
+    return vertices / (resolution - 1.0) * (hi - lo)[None, :] + lo[None, :], triangles
+
+
 class _RenderMSELoss(torch.autograd.Function):
     """pixel + reg terms of BaseNeRF.loss as ONE differentiable op on the fused renderer: forward = render_train_fwd +
     mse_render_loss (which also leaves d/d image, d/d weights_sum), backward = render_train_bwd (+ RegLoss gradient)."""
@@ -262,8 +289,17 @@ class BaseNeRF(nn.Module):
                        os.path.join(save_dir, name) + '.pth')
 
     @staticmethod
-    def save_mesh(*args, **kwargs):
-        raise NotImplementedError('mesh export (marching cubes + trimesh) is outside the accelerated hot paths (SURVEY.md §8 f4)')
+    def save_mesh(save_dir, decoder, code, scene_name, mesh_resolution, mesh_threshold):
+        """base_nerf.py:172-182: density field on the device (`extract_fields`), surface by PyMCubes, file by trimesh -- the two
+        packages the reference uses for this; neither is part of this image, so the call fails loudly when they are missing."""
+        try:
+            import trimesh
+        except ImportError as e:
+            raise ImportError('save_mesh needs `trimesh` (and `mcubes`), like the reference (requirements.txt)') from e
+        os.makedirs(save_dir, exist_ok=True)
+        for code_single, name in zip(code, scene_name):
+            vertices, triangles = extract_geometry(decoder, code_single, mesh_resolution, mesh_threshold)
+            trimesh.Trimesh(vertices, triangles, process=False).export(os.path.join(save_dir, name) + '.stl')
 
     def get_init_code_(self, num_scenes, device=None):
         code_ = torch.empty(self.code_size if num_scenes is None else (num_scenes, *self.code_size), device=device, requires_grad=True,
@@ -760,6 +796,7 @@ class DiffusionNeRF(MultiSceneNeRF):
         if save_dir is not None:
             self.save_scene(save_dir, code, density_grid, density_bitfield, data['scene_name'])
             if self.test_cfg.get('save_mesh', False):
-                self.save_mesh()
+                self.save_mesh(save_dir, decoder, code, data['scene_name'], self.test_cfg.get('mesh_resolution', 256),
+                               self.test_cfg.get('mesh_threshold', 10))
         names = data['scene_name'] if 'scene_name' in data else data['scene_id']
         return dict(log_vars=log_vars, num_samples=len(names), pred_imgs=pred_imgs)

@@ -55,3 +55,21 @@ def test_point_decode_refuses_gradients_and_trainable_decoder(cuda):
     # trainable decoder: the train branch fails loudly (no PyTorch composition in the product)
     with pytest.raises(NotImplementedError):
         dec(torch.zeros(1, 8, 3, device=cuda), torch.ones(1, 8, 3, device=cuda), code.detach(), torch.zeros(1, 64 ** 3 // 8, dtype=torch.uint8, device=cuda), 64)
+
+
+def test_extract_fields_matches_oracle(cuda):
+    """density lattice of nerf_utils.py:64-106 (one native launch) vs the oracle decode; points outside the AABB are zero"""
+    from ssdnerf_b200.nerf import extract_fields
+    g = torch.Generator().manual_seed(9)
+    code = (torch.randn(3, 6, 128, 128, generator=g) * 0.7).clamp(-2, 2)
+    params = rp.make_decoder_params('P', 7)
+    dec = _decoder(params, cuda)
+    R_ = 12
+    with torch.no_grad():
+        u = extract_fields(dec, code.to(cuda), resolution=R_).cpu()
+    ax = torch.linspace(-1.1, 1.1, R_)
+    pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing='ij'), dim=-1).reshape(-1, 3)
+    ref, _ = rp.point_decode(params, pts, None, code, density_only=True)
+    ref = ref.masked_fill(((pts < -1) | (pts > 1)).any(dim=-1), 0).reshape(R_, R_, R_)
+    np.testing.assert_allclose(u.numpy(), ref.numpy(), rtol=2e-4, atol=2e-5)
+    assert float(u[0].abs().max()) == 0.0 and float(u[R_ // 2].max()) > 0
