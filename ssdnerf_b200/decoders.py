@@ -138,6 +138,10 @@ class TriPlaneDecoder(VolumeRenderer):
             raise N.SSDNeRFNativeError('fused renderer covers bilinear / SiLU / trunc_exp / SH-encoded decoders (every reference config)')
         return R.detect_variant(self.decoder_params())
 
+    def refresh_weights(self):
+        """drop the packed weight blob; needed only after parameter writes that bypass `Parameter._version` (`p.data...`)"""
+        self._blob = None
+
     def packed_blob(self):
         key = tuple(p._version for p in self.parameters()) + (str(self.aabb.device),)
         if self._blob is None or self._blob[0] != key:

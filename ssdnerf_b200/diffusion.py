@@ -358,9 +358,13 @@ class GaussianDiffusion(nn.Module):
         if n_lanes < 1 or B % n_lanes or not use_graph:
             n_lanes = 1
         Bl = B // n_lanes
-        key = (id(unet), tuple(p._version for p in unet.parameters()), B, C, H, W, num_steps, clip, clip_range, bool(use_graph), n_lanes)
-        st = self._graphs.get('state')
-        if st is None or st['key'] != key:
+        key = (id(unet), tuple(p._version for p in unet.parameters()), str(dev), B, C, H, W, num_steps, clip, clip_range, bool(use_graph), n_lanes)
+        # one captured state per (device, batch shape, sampler settings); a ragged last batch alternates between two entries instead of
+        # re-capturing.  Stale entries (changed weights) and anything beyond 4 entries are dropped, oldest first.
+        for k in [k for k in self._graphs if k[0] == id(unet) and k[1] != key[1]]:
+            del self._graphs[k]
+        st = self._graphs.get(key)
+        if st is None:
             from .unet import UNetEngine
             ts = self.ddim_timesteps(num_steps)
             lanes = []
@@ -374,7 +378,9 @@ class GaussianDiffusion(nn.Module):
                       # host-side precompute (no x dependence): coefficient rows + every step's scale/shift projections
                       coef=self.ddim_coefficients(ts, eta).to(dev),
                       ss_table=lanes[0]['eng'].scale_shift_rows(unet.embedding(ts.to(dev))).contiguous())          # [S, ss_total]
-            self._graphs['state'] = st
+            while len(self._graphs) >= 4:
+                del self._graphs[next(iter(self._graphs))]
+            self._graphs[key] = st
         coef, ss_table, S, lanes = st['coef'], st['ss_table'], st['S'], st['lanes']
         L = N.lib()
 
@@ -435,6 +441,12 @@ class GaussianDiffusion(nn.Module):
         for ln in lanes:
             cur.wait_stream(ln['stream'])
         return torch.cat([ln['x_t'] for ln in lanes], dim=0)
+
+    def refresh_weights(self):
+        """drop every captured graph and the denoiser's packed weights (after parameter writes that bypass `Parameter._version`)"""
+        self._graphs.clear()
+        if hasattr(self.denoising, 'refresh_weights'):
+            self.denoising.refresh_weights()
 
     def sample_from_noise(self, noise, **kwargs):
         fn = getattr(self, f'{self.sample_method.lower()}_sample', None)

@@ -182,6 +182,13 @@ class DenoisingUnetMod(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def refresh_weights(self):
+        """Drop the packed fp16 weights (and with them every captured DDIM graph keyed on this engine).  The caches follow
+        `Parameter._version`, which `load_state_dict` / optimizers / in-place ops bump; writes through `.data` (e.g. an EMA hook doing
+        `p.data.lerp_()`) do NOT -- call this after such an update."""
+        self._engine = None
+        self._engine_key = None
+
     def embedding(self, t):
         if self.use_rescale_timesteps:
             t = t.float() * (1000.0 / self.num_timesteps)
@@ -375,6 +382,8 @@ class UNetEngine:
         if 'ws' in d:
             sc = U.conv3x3_f16(x, d['ws'].unsqueeze(0), cout, bias=d['wsb'], x2=sk, taps=1, out=self._buf(('sc', H, cout), (B, H, W, cout)))
         else:
+            if sk is not None:      # an identity shortcut over a channel concat would need the concatenated tensor (mmgen adds it whole);
+                raise NotImplementedError('ResBlock with a skip concat but no shortcut convolution (cin + skip == cout) is not built')
             sc = x
         qh1 = self._q(('h1', tag), cout)
         qo = self._q(('res_out', tag), cout)
