@@ -355,7 +355,7 @@ def run_ours(args):
     unet_flops = UNET_FLOP_PER_SAMPLE_STEP * B * DDIM_STEPS            # per rank per step
     tf_achieved = unet_flops / (ddim_ms * 1e-3) / 1e12
     render_bytes = (samples_all / world) * RAY_GATHER_BYTES_PER_SAMPLE + rays * RAY_IO_BYTES
-    kern_p = os.environ.get('SSDNERF_BENCH_KERNEL_P', 'k_render_p2')
+    kern_p = os.environ.get('SSDNERF_BENCH_KERNEL_P', 'k_render_p3')
     traffic, traffic_src = measured_traffic(kern_p, rays)
     gather_bytes = B * V * IMG * IMG * 3 * world if world > 1 else 0
     line = {

@@ -194,5 +194,8 @@ def test_stride2_conv_and_upsample_conv_without_intermediate_buffers(cuda, B, H,
     assert y2.shape == ref2.shape
     assert (y2.float() - ref2).abs().max().item() < 3e-3 * ref2.abs().max().item() + 3e-3
     assert float((y2.float() - ref2).norm() / ref2.norm()) < 1e-3
-    rq2 = ref2.reshape(B, -1, Cout // 4, 4)
-    torch.testing.assert_close(q2, torch.stack([rq2.sum(dim=(1, 3)), (rq2 * rq2).sum(dim=(1, 3))], dim=-1), rtol=3e-3, atol=5e-2)
+    # the fused statistics are those of the kernel's own fp32 accumulators (merged fp16 weights), summed over the four phase launches
+    o2 = U.upconv3x3_f16(x, U.pack_upconv_weight(w).to(cuda), Cout, bias=bias, out=torch.empty(B, 2 * H, 2 * H, Cout, dtype=torch.float32, device=cuda))
+    assert torch.equal(y2, o2.half())
+    rq2 = o2.reshape(B, -1, Cout // 4, 4)
+    torch.testing.assert_close(q2, torch.stack([rq2.sum(dim=(1, 3)), (rq2 * rq2).sum(dim=(1, 3))], dim=-1), rtol=1e-3, atol=2e-2)
