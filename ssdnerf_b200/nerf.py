@@ -336,32 +336,32 @@ class BaseNeRF(nn.Module):
             return [cls(o, **scfg) for o in code_optimizer]
         return cls(code_optimizer, **scfg)
 
-    # ------------------------------------------------------------------ ray batches (base_nerf.py:231-274)
+    # ------------------------------------------------------------------ ray batches (contract of base_nerf.py:231-274)
+    @staticmethod
+    def _scene_permutations(num_scenes, length, device):
+        """one independent random permutation of range(length) per scene, [num_scenes, length] (one randperm draw per scene, scene order)"""
+        return torch.stack([torch.randperm(length, device=device) for _ in range(num_scenes)])
+
     @staticmethod
     def ray_sample(cond_rays_o, cond_rays_d, cond_imgs, n_samples, sample_inds=None):
-        device = cond_rays_o.device
-        num_scenes, num_imgs, h, w, _ = cond_rays_o.size()
-        num_scene_pixels = num_imgs * h * w
-        rays_o = cond_rays_o.reshape(num_scenes, num_scene_pixels, 3)
-        rays_d = cond_rays_d.reshape(num_scenes, num_scene_pixels, 3)
-        target_rgbs = cond_imgs.reshape(num_scenes, num_scene_pixels, 3)
-        if num_scene_pixels > n_samples:
-            if sample_inds is None:
-                sample_inds = torch.stack([torch.randperm(num_scene_pixels, device=device)[:n_samples] for _ in range(num_scenes)], dim=0)
-            scene_arange = torch.arange(num_scenes, device=device)[:, None]
-            rays_o, rays_d, target_rgbs = rays_o[scene_arange, sample_inds], rays_d[scene_arange, sample_inds], target_rgbs[scene_arange, sample_inds]
-        return rays_o, rays_d, target_rgbs
+        """[B,V,h,w,3] rays / colours -> per-scene batches [B,n,3]; all pixels when a scene has no more than n_samples of them"""
+        flat = [t.reshape(t.size(0), -1, 3) for t in (cond_rays_o, cond_rays_d, cond_imgs)]
+        pixels = flat[0].size(1)
+        if pixels <= n_samples:
+            return tuple(flat)
+        if sample_inds is None:
+            sample_inds = BaseNeRF._scene_permutations(flat[0].size(0), pixels, cond_rays_o.device)[:, :n_samples]
+        pick = sample_inds.unsqueeze(-1).expand(-1, -1, 3)
+        return tuple(t.gather(1, pick) for t in flat)
 
     @staticmethod
     def get_raybatch_inds(cond_imgs, n_inverse_rays):
-        device = cond_imgs.device
-        num_scenes, num_imgs, h, w, _ = cond_imgs.size()
-        num_scene_pixels = num_imgs * h * w
-        if num_scene_pixels > n_inverse_rays:
-            raybatch_inds = torch.stack([torch.randperm(num_scene_pixels, device=device) for _ in range(num_scenes)], dim=0)
-            raybatch_inds = raybatch_inds.split(n_inverse_rays, dim=1)
-            return raybatch_inds, len(raybatch_inds)
-        return None, None
+        """-> (tuple of index batches [B, <= n_inverse_rays] covering every pixel once, their number), or (None, None) when one batch holds all"""
+        pixels = cond_imgs[0].numel() // 3
+        if pixels <= n_inverse_rays:
+            return None, None
+        batches = BaseNeRF._scene_permutations(cond_imgs.size(0), pixels, cond_imgs.device).split(n_inverse_rays, dim=1)
+        return batches, len(batches)
 
     # ------------------------------------------------------------------ losses (base_nerf.py:276-316)
     def loss(self, decoder, code, density_bitfield, target_rgbs, rays_o, rays_d, dt_gamma=0.0, return_decoder_loss=False,
@@ -450,25 +450,20 @@ class BaseNeRF(nn.Module):
         prev = decoder.training
         decoder.train(True)
         with module_requires_grad(decoder, False), torch.enable_grad():
-            n_inverse_steps = cfg.get('n_inverse_steps', 1000)
-            n_inverse_rays = cfg.get('n_inverse_rays', 4096)
-            num_scenes, num_imgs, h, w, _ = cond_imgs.size()
-            num_scene_pixels = num_imgs * h * w
+            n_inverse_steps, n_inverse_rays = cfg.get('n_inverse_steps', 1000), cfg.get('n_inverse_rays', 4096)
+            assert n_inverse_steps > 0
+            num_scenes = cond_imgs.size(0)
+            num_scene_pixels = cond_imgs[0].numel() // 3
             raybatch_inds, num_raybatch = self.get_raybatch_inds(cond_imgs, n_inverse_rays)
-            if code_ is None:
-                code_ = self.get_init_code_(num_scenes, device=device)
-            if density_grid is None:
-                density_grid = self.get_init_density_grid(num_scenes, device)
-            if density_bitfield is None:
-                density_bitfield = self.get_init_density_bitfield(num_scenes, device)
-            if iter_density is None:
-                iter_density = 0
+            # defaults: fresh latent / empty occupancy state / optimiser + schedule from cfg
+            code_ = self.get_init_code_(num_scenes, device=device) if code_ is None else code_
+            density_grid = self.get_init_density_grid(num_scenes, device) if density_grid is None else density_grid
+            density_bitfield = self.get_init_density_bitfield(num_scenes, device) if density_bitfield is None else density_bitfield
+            iter_density = 0 if iter_density is None else iter_density
             if code_optimizer is None:
                 assert code_scheduler is None
                 code_optimizer = self.build_optimizer(code_, cfg)
-            if code_scheduler is None:
-                code_scheduler = self.build_scheduler(code_optimizer, cfg)
-            assert n_inverse_steps > 0
+            code_scheduler = self.build_scheduler(code_optimizer, cfg) if code_scheduler is None else code_scheduler
             optimizers = code_optimizer if isinstance(code_optimizer, list) else [code_optimizer]
             schedulers = [] if code_scheduler is None else (code_scheduler if isinstance(code_scheduler, list) else [code_scheduler])
             for step in range(n_inverse_steps):
@@ -615,20 +610,13 @@ class DiffusionNeRF(MultiSceneNeRF):
 
     # ------------------------------------------------------------------ code <-> diffusion layout (diffusion_nerf.py:50-64)
     def code_diff_pr(self, code):
-        code_diff = code
-        if self.code_permute is not None:
-            code_diff = code_diff.permute([0] + [axis + 1 for axis in self.code_permute])
-        if self.code_reshape is not None:
-            code_diff = code_diff.reshape(code.size(0), *self.code_reshape)
-        return code_diff
+        """scene code [B, *code_size] -> the denoiser's layout: optional axis permutation (batch axis kept), then reshape"""
+        out = code if self.code_permute is None else code.permute(0, *(a + 1 for a in self.code_permute))
+        return out if self.code_reshape is None else out.reshape(code.size(0), *self.code_reshape)
 
     def code_diff_pr_inv(self, code_diff):
-        code = code_diff
-        if self.code_reshape is not None:
-            code = code.reshape(code.size(0), *self.code_reshape_inv)
-        if self.code_permute_inv is not None:
-            code = code.permute([0] + [axis + 1 for axis in self.code_permute_inv])
-        return code
+        out = code_diff if self.code_reshape is None else code_diff.reshape(code_diff.size(0), *self.code_reshape_inv)
+        return out if self.code_permute_inv is None else out.permute(0, *(a + 1 for a in self.code_permute_inv))
 
     def _modules_for_eval(self):
         return (self.diffusion_ema if self.diffusion_use_ema else self.diffusion,
