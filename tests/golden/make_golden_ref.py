@@ -16,6 +16,11 @@ is gone from NumPy 2), so this script loads three of its files BY PATH with the 
         prepare_diffusion_vars (:131-154, with `np.cumproduct = np.cumprod` patched in), pred_x_0 (:180-240, incl. both
         guidance branches), p_sample_langevin (:242-262), p_sample_ddim (:264-293), ddim_sample (:295-331), q_sample (:166-178)
     lib/models/diffusions/sampler.py          : SNRWeightedTimeStepSampler.__init__ (:15-46: the per-timestep loss weights)
+    lib/core/utils/nerf_utils.py              : get_ray_directions / get_rays / get_cam_rays (:17-61) (mcubes stubbed, unused)
+    lib/ops/activation.py                     : _trunc_exp forward / backward (:8-23)
+    lib/models/losses/reg_loss.py, tv_loss.py : RegLoss, TVLoss (mmgen `weighted_loss` decorator stubbed: mean reduction)
+    lib/models/autodecoders/base_nerf.py      : TanhCode, NormalizedTanhCode (:25-76), BaseNeRF.ray_sample / get_raybatch_inds (:231-274) with
+        seeded CPU randperm draws (matplotlib / lpips / trimesh / mmcv.runner / lib.core / lib.ops stubbed: none of them is touched)
     lib/models/losses/ddpm_loss.py            : DDPMMSELossMod (:12-131: 0.5 * flat-mean MSE, weight[t] * weight_scale rescale, norm_factor)
         driven by gaussian_diffusion.py forward_train / loss (:404-450) with the timestep draw and the noise injected
 
@@ -315,6 +320,92 @@ def _load(relpath, name):
     return m
 
 
+def weighted_loss(fn):
+    """mmgen.models.losses.utils.weighted_loss [mmgen-memory]: elementwise weight, then 'mean' (or sum / avg_factor) reduction"""
+    def wrapper(*args, weight=None, reduction='mean', avg_factor=None, **kwargs):
+        loss = fn(*args, **kwargs)
+        if weight is not None:
+            loss = loss * weight
+        if avg_factor is not None:
+            return loss.sum() / avg_factor
+        return loss.mean() if reduction == 'mean' else (loss.sum() if reduction == 'sum' else loss)
+    return wrapper
+
+
+def load_reference_host_helpers():
+    """nerf_utils.py, activation.py, reg_loss.py, tv_loss.py, base_nerf.py of the reference, executed from /root/reference"""
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    mod('mcubes')
+    nu = _load('lib/core/utils/nerf_utils.py', 'ref_nerf_utils')
+    act = _load('lib/ops/activation.py', 'ref_activation')
+    mod('mmgen.models.losses.utils', weighted_loss=weighted_loss)
+    reg = _load('lib/models/losses/reg_loss.py', 'ref_reg_loss')
+    tv = _load('lib/models/losses/tv_loss.py', 'ref_tv_loss')
+    # base_nerf.py: heavy imports that its code-activation classes and static ray helpers never touch
+    mod('matplotlib'); mod('matplotlib.pyplot'); mod('lpips'); mod('trimesh')
+    mod('mmcv.runner', load_checkpoint=None)
+    sys.modules['mmcv'].runner = sys.modules['mmcv.runner']
+    names = ('custom_meshgrid', 'eval_psnr', 'eval_ssim_skimage', 'rgetattr', 'rsetattr', 'extract_geometry', 'module_requires_grad')
+    core = sys.modules['reflib.core']
+    for n in names:
+        setattr(core, n, None)
+    core.get_cam_rays = nu.get_cam_rays
+    mod('lib'); mod('lib.ops', morton3D=None, morton3D_invert=None, packbits=None)
+    for name in ('reflib.models.autodecoders',):
+        sys.modules[name] = types.ModuleType(name); sys.modules[name].__path__ = []
+    base = _load('lib/models/autodecoders/base_nerf.py', 'reflib.models.autodecoders.base_nerf')
+    return nu, act, reg, tv, base
+
+
+def host_helper_fixtures(out):
+    nu, act, reg, tv, base = load_reference_host_helpers()
+    g = torch.Generator().manual_seed(21)
+    # cameras -> rays
+    R_ = torch.linalg.qr(torch.randn(2, 2, 3, 3, generator=g))[0]
+    c2w = torch.cat([torch.cat([R_, torch.randn(2, 2, 3, 1, generator=g)], dim=-1), torch.tensor([0., 0, 0, 1]).expand(2, 2, 1, 4)], dim=-2)
+    intr = torch.tensor([[[40.0, 41.0, 15.5, 16.25], [131.25, 131.25, 64.0, 64.0]]]).repeat(2, 1, 1)
+    ro, rd = nu.get_cam_rays(c2w, intr, 6, 5)
+    out['cam_c2w'], out['cam_intr'], out['cam_rays_o'], out['cam_rays_d'] = c2w.numpy(), intr.numpy(), ro.contiguous().numpy(), rd.numpy()
+    # trunc_exp forward / backward
+    x = torch.tensor([-30.0, -14.0, -1.0, 0.0, 0.5, 3.0, 14.0, 30.0], requires_grad=True)
+    y = act.trunc_exp(x)
+    y.backward(torch.ones_like(y))
+    out['trunc_exp_x'], out['trunc_exp_y'], out['trunc_exp_grad'] = x.detach().numpy(), y.detach().numpy(), x.grad.numpy()
+    # latent regularisers
+    code = torch.randn(2, 3, 6, 8, 8, generator=g)
+    out['loss_code'] = code.numpy()
+    out['reg_loss_p2'] = np.array(float(reg.RegLoss(power=2, loss_weight=3e-3)(code)))
+    out['reg_loss_p1'] = np.array(float(reg.RegLoss(power=1, loss_weight=0.5)(code)))
+    out['tv_loss_p15'] = np.array(float(tv.TVLoss(power=1.5, loss_weight=1.0)(code)))
+    # code activations
+    z = torch.randn(3, 6, 4, 4, generator=g) * 1.5
+    out['act_z'] = z.numpy()
+    t2 = base.TanhCode(scale=2)
+    out['tanh2_fwd'], out['tanh2_inv'] = t2(z).numpy(), t2.inverse(t2(z) * 0.9).numpy()
+    nt = base.NormalizedTanhCode(mean=0.0, std=0.5, clip_range=2)
+    nt.running_mean.fill_(0.1); nt.running_var.fill_(0.3)
+    out['ntanh_fwd'], out['ntanh_inv'] = nt(z).numpy(), nt.inverse(nt(z) * 0.9).numpy()
+    nt.train()
+    nt(z, update_stats=True)
+    out['ntanh_running_mean_after'], out['ntanh_running_var_after'] = nt.running_mean.numpy().copy(), nt.running_var.numpy().copy()
+    # ray batches: seeded CPU randperm draws
+    imgs = torch.rand(2, 3, 4, 4, 3, generator=g)
+    rays_o, rays_d = torch.rand(2, 3, 4, 4, 3, generator=g), torch.rand(2, 3, 4, 4, 3, generator=g)
+    out['rb_imgs'], out['rb_rays_o'], out['rb_rays_d'] = imgs.numpy(), rays_o.numpy(), rays_d.numpy()
+    torch.manual_seed(123)
+    inds, nb = base.BaseNeRF.get_raybatch_inds(imgs, 20)
+    out['rb_inds'], out['rb_num'] = torch.cat(list(inds), dim=1).numpy(), np.array(nb)
+    torch.manual_seed(321)
+    o, d, t = base.BaseNeRF.ray_sample(rays_o, rays_d, imgs, 10)
+    out['rs_o'], out['rs_d'], out['rs_t'] = o.numpy(), d.numpy(), t.numpy()
+    o, d, t = base.BaseNeRF.ray_sample(rays_o, rays_d, imgs, 20, sample_inds=inds[1])
+    out['rs_o_given'], out['rs_t_given'] = o.numpy(), t.numpy()
+
+
 def load_reference():
     """-> (modules.py, denoising.py, gaussian_diffusion.py, sampler.py) of the reference, executed from /root/reference."""
     _install_stubs()
@@ -440,6 +531,7 @@ def main():
     eps = torch.randn(2, 18, 16, 16, generator=g)
     xq, mean, std = diff.q_sample(target, torch.tensor([10, 900]), noise=eps)
     out['q_eps'], out['q_sample'] = eps.numpy(), xq.numpy()
+    host_helper_fixtures(out)
     out['unet_weight_seed'] = np.array(11)
     out['unet_weight_checksum'] = np.array(sum(float(v.double().sum()) for v in sd.values()))
     # ---- diffusion loss as val_optim uses it (chairs_recons1v settings: SNR power 0.25, v-target, weight_scale, scale_norm)

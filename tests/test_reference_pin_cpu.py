@@ -185,3 +185,45 @@ def test_diffusion_prior_loss_matches_reference(ref):
     assert m.diffusion_ema.ddpm_loss.weight_scale == 1.0 and m.diffusion.ddpm_loss.weight_scale == 4.0
     m.train()
     assert m.diffusion_ema.ddpm_loss.weight_scale == 4.0
+
+
+def test_host_helpers_match_reference_executed(ref):
+    """fixtures produced by executing the reference's nerf_utils.get_cam_rays, activation._trunc_exp, RegLoss / TVLoss, TanhCode /
+    NormalizedTanhCode and BaseNeRF.ray_sample / get_raybatch_inds (seeded CPU randperm draws)"""
+    from oracle import render_port as rp
+    from ssdnerf_b200.activation import trunc_exp
+    from ssdnerf_b200.nerf import BaseNeRF, NormalizedTanhCode, RegLoss, TanhCode, TVLoss
+    # cameras -> rays: the oracle restatement the GPU kernel (ssdnerf_cam_rays / in-kernel make_ray) is tested against
+    ro, rd = rp.get_cam_rays(torch.from_numpy(ref['cam_c2w']), torch.from_numpy(ref['cam_intr']), 6, 5)
+    assert np.array_equal(ro.numpy(), ref['cam_rays_o'])
+    _close(rd, ref['cam_rays_d'], 2e-7)
+    # trunc_exp: exp forward (no clamp), gradient clamped to [1e-6, 1e6]
+    x = torch.from_numpy(ref['trunc_exp_x']).clone().requires_grad_(True)
+    y = trunc_exp(x)
+    y.backward(torch.ones_like(y))
+    assert np.array_equal(y.detach().numpy(), ref['trunc_exp_y']) and np.array_equal(x.grad.numpy(), ref['trunc_exp_grad'])
+    # regularisers of the latent
+    code = torch.from_numpy(ref['loss_code'])
+    assert abs(float(RegLoss(power=2, loss_weight=3e-3)(code)) - float(ref['reg_loss_p2'])) < 1e-9
+    assert abs(float(RegLoss(power=1, loss_weight=0.5)(code)) - float(ref['reg_loss_p1'])) < 1e-7
+    assert abs(float(TVLoss(power=1.5, loss_weight=1.0)(code)) - float(ref['tv_loss_p15'])) < 1e-6
+    # code activations
+    z = torch.from_numpy(ref['act_z'])
+    t2 = TanhCode(scale=2)
+    _close(t2(z), ref['tanh2_fwd'], 1e-6); _close(t2.inverse(t2(z) * 0.9), ref['tanh2_inv'], 1e-5)
+    nt = NormalizedTanhCode(mean=0.0, std=0.5, clip_range=2)
+    nt.running_mean.fill_(0.1); nt.running_var.fill_(0.3)
+    _close(nt(z), ref['ntanh_fwd'], 1e-6); _close(nt.inverse(nt(z) * 0.9), ref['ntanh_inv'], 1e-5)
+    nt.train()
+    nt(z, update_stats=True)
+    _close(nt.running_mean, ref['ntanh_running_mean_after'], 1e-7); _close(nt.running_var, ref['ntanh_running_var_after'], 1e-7)
+    # ray batches: same randperm draws in the same order as the reference
+    imgs, rays_o, rays_d = (torch.from_numpy(ref[k]) for k in ('rb_imgs', 'rb_rays_o', 'rb_rays_d'))
+    torch.manual_seed(123)
+    inds, nb = BaseNeRF.get_raybatch_inds(imgs, 20)
+    assert nb == int(ref['rb_num']) and np.array_equal(torch.cat(list(inds), dim=1).numpy(), ref['rb_inds'])
+    torch.manual_seed(321)
+    o, d, t = BaseNeRF.ray_sample(rays_o, rays_d, imgs, 10)
+    assert np.array_equal(o.numpy(), ref['rs_o']) and np.array_equal(d.numpy(), ref['rs_d']) and np.array_equal(t.numpy(), ref['rs_t'])
+    o, d, t = BaseNeRF.ray_sample(rays_o, rays_d, imgs, 20, sample_inds=inds[1])
+    assert np.array_equal(o.numpy(), ref['rs_o_given']) and np.array_equal(t.numpy(), ref['rs_t_given'])
