@@ -173,7 +173,7 @@ SSDNERF_API int ssdnerf_render_fwd(const ssdnerf_render_args* args, void* stream
  *    backward: re-marches the same samples, applies K8 with the saved weights_sum / image and
  *              accumulates d(loss)/d(planes) into grad_planes (channels-last, layout of ssdnerf_pack_planes,
  *              caller zero-fills); ssdnerf_unpack_plane_grads converts to the [B][3][6][H][W] code layout.
- *    The decoder weights receive no gradient (frozen decoder, diffusion_nerf.py:273).
+ *    The decoder weights receive a gradient only when grad_decoder_blob is given (frozen decoder otherwise, diffusion_nerf.py:273).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct ssdnerf_render_train_args {
     int variant;               /* SSDNERF_DEC_P */
@@ -197,6 +197,9 @@ typedef struct ssdnerf_render_train_args {
     const float* grad_image;   /* [B][N][3] backward: in */
     float* grad_planes;        /* [B][3][H][W][8] fp32, backward: accumulated into */
     uint32_t* counter;         /* 4 bytes of device scratch (tile counter) */
+    float* grad_decoder_blob;  /* backward, optional: [ssdnerf_decoder_blob_floats(SSDNERF_DEC_P)] fp32, accumulated into --
+                                  d(loss)/d(decoder weights) in the layout of decoder_blob (trainable decoder:
+                                  lib/models/autodecoders/multiscene_nerf.py:203-207 loss.backward() + decoder optimizer step) */
 } ssdnerf_render_train_args;
 
 /* lib/core/utils/nerf_utils.py:17-61 get_cam_rays: poses [B][V][4][4] c2w, intrinsics [B][V][4] -> rays_o / rays_d [B][V][h][w][3] */

@@ -54,7 +54,7 @@ class RenderTrainArgs(ctypes.Structure):
         ('max_steps', c_u32),
         ('weights_sum', c_void_p), ('depth', c_void_p), ('image', c_void_p), ('num_samples', c_void_p),
         ('grad_ws', c_void_p), ('grad_image', c_void_p), ('grad_planes', c_void_p),
-        ('counter', c_void_p),
+        ('counter', c_void_p), ('grad_decoder_blob', c_void_p),
     ]
 
 

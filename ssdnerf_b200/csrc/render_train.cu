@@ -35,6 +35,7 @@ struct TrainParams {
     float* weights_sum; float* depth; float* image; int32_t* num_samples;
     const float* grad_ws; const float* grad_image;
     float* grad_planes;                     // [B][3][H][W][8] fp32, accumulated into
+    float* grad_blob;                       // [DecP::BLOB] fp32 decoder-weight gradients in blob layout, accumulated into (WG kernel)
     uint32_t* counter;
 };
 
@@ -48,7 +49,29 @@ struct SmemT {
     float bd, bc[3], sat;
     float4 w1t[DecP::HID][5];               // backward only: W1 transposed, [o][k] padded to 20
     float hid[DecP::HID][kCtaThreads];      // backward only: base_x pre-activations of this thread's sample
+    float wg[DecP::BLOB];                   // weight-gradient kernel only: per-CTA partial sums in blob layout
 };
+
+// Sum N per-lane values across the warp with N-1 + log2(32/N) shuffles (recursive halving): on return lane l holds the
+// warp total of v[l / (32 / N)].  All 32 lanes must call.
+template <int N>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane) {
+    static_assert(N == 32 || N == 16 || N == 8 || N == 4, "N must be a power of two in [4, 32]");
+#pragma unroll
+    for (int half = N / 2, m = 16; half >= 1; half >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int m = 16 / N; m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -80,8 +103,12 @@ __device__ __forceinline__ void scatter_plane_p(float* __restrict__ gplane, uint
     }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(kCtaThreads, BWD ? 2 : 3) k_render_train_p(TrainParams p) {
+// WG (implies BWD): additionally accumulate d(loss)/d(decoder weights) -- the reference obtains these from autograd over the
+// materialised per-sample activations (base_volume_renderer.py:59-77 + triplane_decoder.py:119-179); here each warp reduces the
+// 2572 outer-product terms of its 32 samples with recursive-halving shuffles into a per-CTA shared-memory copy of the blob.
+template <bool BWD, bool WG>
+__global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_train_p(TrainParams p) {
+    static_assert(BWD || !WG, "weight gradients are part of the backward pass");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemT& s = *reinterpret_cast<SmemT*>(smem_raw);
     {
@@ -103,6 +130,7 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? 2 : 3) k_render_train_p(Tra
                 w1t[i] = k < DecP::KF ? __ldg(blob + DecP::OFF_W1 + k * DecP::HID + o) : 0.0f;
             }
         }
+        if (WG) for (int i = threadIdx.x; i < DecP::BLOB; i += kCtaThreads) s.wg[i] = 0.0f;
         if (threadIdx.x == 0) {
             s.bd = __ldg(blob + DecP::OFF_BD);
             s.bc[0] = __ldg(blob + DecP::OFF_BC); s.bc[1] = __ldg(blob + DecP::OFF_BC + 1); s.bc[2] = __ldg(blob + DecP::OFF_BC + 2);
@@ -134,8 +162,8 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? 2 : 3) k_render_train_p(Tra
         MarchCfg c = p.cfg;
         if (p.dt_gamma) c.dt_gamma = __ldg(p.dt_gamma + scene);
 
+        float sh[16];
         {   // per-ray dir_net(SH16(d)) -> this thread's shared-memory column
-            float sh[16];
             sh16(r.dx, r.dy, r.dz, sh);
 #pragma unroll 4
             for (int o4 = 0; o4 < DecP::HID / 4; ++o4) {
@@ -176,9 +204,11 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? 2 : 3) k_render_train_p(Tra
                 has = probe(c, r, grid, t, x, y, z, dt, vi);
             }
             if (!__any_sync(0xffffffffu, has)) break;
+            float f[DecP::KF];
+            bool gv = false;                               // this lane's sample receives a gradient (K8 wrote one for it)
+            float gsd = 0.0f, gp0 = 0.0f, gp1 = 0.0f, gp2 = 0.0f;
             if (has) {
                 // ---- decode (triplane_decoder.py:119-179)
-                float f[DecP::KF];
                 gather_plane_p(planes, p.plane_h, p.plane_w, x, y, f);
                 gather_plane_p(planes + plane_stride, p.plane_h, p.plane_w, x, z, f + 6);
                 gather_plane_p(planes + 2 * plane_stride, p.plane_h, p.plane_w, y, z, f + 12);
@@ -231,35 +261,74 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? 2 : 3) k_render_train_p(Tra
                         const float gsig = dt * (gi0 * (T * sr - (r_fin - cr)) + gi1 * (T * sg - (g_fin - cg)) + gi2 * (T * sb - (b_fin - cb)) +
                                                  gws * (1.0f - ws_fin));
                         // sigmoid (+ saturation affine) and trunc_exp backward (lib/ops/activation.py:17-20)
-                        const float gp0 = grr * k1 * s0 * (1.0f - s0), gp1 = grg * k1 * s1 * (1.0f - s1), gp2 = grb * k1 * s2 * (1.0f - s2);
-                        const float gsd = gsig * fminf(fmaxf(sigma, 1e-6f), 1e6f);
-                        // hidden layer (d/d base_x through both SiLU branches) fused with the transposed input layer
-                        //   g_f[k] = sum_o W1[k][o] * g_base[o]
-                        float gf[20];
-#pragma unroll
-                        for (int k = 0; k < 20; ++k) gf[k] = 0.0f;
-#pragma unroll 4
-                        for (int o = 0; o < DecP::HID; ++o) {
-                            const float bx = s.hid[o][tid];
-                            const float u = bx + s.dirf[o][tid];
-                            const float4 hw = s.heads[o];
-                            const float sa = sigmoid_f(bx), su = sigmoid_f(u);
-                            const float da = sa * fmaf(bx, 1.0f - sa, 1.0f), du = su * fmaf(u, 1.0f - su, 1.0f);
-                            const float gc = fmaf(hw.y, gp0, fmaf(hw.z, gp1, hw.w * gp2));
-                            const float gb = fmaf(gc, du, hw.x * gsd * da);
-#pragma unroll
-                            for (int q = 0; q < 5; ++q) {
-                                const float4 wv = s.w1t[o][q];
-                                gf[4 * q] = fmaf(wv.x, gb, gf[4 * q]); gf[4 * q + 1] = fmaf(wv.y, gb, gf[4 * q + 1]);
-                                if (q < 4) { gf[4 * q + 2] = fmaf(wv.z, gb, gf[4 * q + 2]); gf[4 * q + 3] = fmaf(wv.w, gb, gf[4 * q + 3]); }
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < DecP::KF; ++k) f[k] = gf[k];
-                        scatter_plane_p(gplanes, p.plane_h, p.plane_w, x, y, f);
-                        scatter_plane_p(gplanes + plane_stride, p.plane_h, p.plane_w, x, z, f + 6);
-                        scatter_plane_p(gplanes + 2 * plane_stride, p.plane_h, p.plane_w, y, z, f + 12);
+                        gp0 = grr * k1 * s0 * (1.0f - s0); gp1 = grg * k1 * s1 * (1.0f - s1); gp2 = grb * k1 * s2 * (1.0f - s2);
+                        gsd = gsig * fminf(fmaxf(sigma, 1e-6f), 1e6f);
+                        gv = true;
                     }
+                }
+            }
+            // ---- MLP backward.  Without WG only the lanes that hold a gradient run it; with WG the whole warp does (the weight-gradient
+            //      reduction is a warp collective) and lanes without one contribute exact zeros.
+            if (BWD && (WG || gv)) {
+                if (WG && !gv) {
+#pragma unroll
+                    for (int k = 0; k < DecP::KF; ++k) f[k] = 0.0f;
+                }
+                // hidden layer (d/d base_x through both SiLU branches) fused with the transposed input layer
+                //   g_f[k] = sum_o W1[k][o] * g_base[o]
+                float gf[20];
+#pragma unroll
+                for (int k = 0; k < 20; ++k) gf[k] = 0.0f;
+#pragma unroll 4
+                for (int o = 0; o < DecP::HID; ++o) {
+                    const float bx = (WG && !gv) ? 0.0f : s.hid[o][tid];
+                    const float u = bx + s.dirf[o][tid];
+                    const float4 hw = s.heads[o];
+                    const float sa = sigmoid_f(bx), su = sigmoid_f(u);
+                    const float da = sa * fmaf(bx, 1.0f - sa, 1.0f), du = su * fmaf(u, 1.0f - su, 1.0f);
+                    const float gc = fmaf(hw.y, gp0, fmaf(hw.z, gp1, hw.w * gp2));
+                    const float gd = gc * du;                          // d/d dir_net pre-activation
+                    const float gb = fmaf(hw.x * gsd, da, gd);         // d/d base_net pre-activation
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const float4 wv = s.w1t[o][q];
+                        gf[4 * q] = fmaf(wv.x, gb, gf[4 * q]); gf[4 * q + 1] = fmaf(wv.y, gb, gf[4 * q + 1]);
+                        if (q < 4) { gf[4 * q + 2] = fmaf(wv.z, gb, gf[4 * q + 2]); gf[4 * q + 3] = fmaf(wv.w, gb, gf[4 * q + 3]); }
+                    }
+                    if (WG) {
+                        // 40 outer-product terms of hidden unit o: W1[0..17][o], Wdir[0..15][o], Wd[o], Wc[0..2][o], b1[o], bdir[o]
+                        float v32[32];
+#pragma unroll
+                        for (int k = 0; k < DecP::KF; ++k) v32[k] = f[k] * gb;
+#pragma unroll
+                        for (int j = 0; j < 14; ++j) v32[DecP::KF + j] = sh[j] * gd;
+                        const float hact = u * su;
+                        float v8[8] = {sh[14] * gd, sh[15] * gd, bx * sa * gsd, hact * gp0, hact * gp1, hact * gp2, gb, gd};
+                        const float t32 = warp_reduce_scatter<32>(v32, lane);      // lane l: term l
+                        const float t8 = warp_reduce_scatter<8>(v8, lane);         // lane l: term l >> 2
+                        const int i32 = lane < DecP::KF ? DecP::OFF_W1 + lane * DecP::HID : DecP::OFF_WDIR + (lane - DecP::KF) * DecP::HID;
+                        atomicAdd(&s.wg[i32 + o], t32);
+                        if ((lane & 3) == 0) {
+                            const int q = lane >> 2;
+                            const int i8 = q < 2 ? DecP::OFF_WDIR + (14 + q) * DecP::HID
+                                         : q == 2 ? DecP::OFF_WD
+                                         : q < 6 ? DecP::OFF_WC + (q - 3) * DecP::HID
+                                         : q == 6 ? DecP::OFF_B1 : DecP::OFF_BDIR;
+                            atomicAdd(&s.wg[i8 + o], t8);
+                        }
+                    }
+                }
+                if (gv) {
+#pragma unroll
+                    for (int k = 0; k < DecP::KF; ++k) f[k] = gf[k];
+                    scatter_plane_p(gplanes, p.plane_h, p.plane_w, x, y, f);
+                    scatter_plane_p(gplanes + plane_stride, p.plane_h, p.plane_w, x, z, f + 6);
+                    scatter_plane_p(gplanes + 2 * plane_stride, p.plane_h, p.plane_w, y, z, f + 12);
+                }
+                if (WG) {                                              // head biases: bd, bc[0..2]
+                    float v4[4] = {gsd, gp0, gp1, gp2};
+                    const float t4 = warp_reduce_scatter<4>(v4, lane);  // lane l: term l >> 3
+                    if ((lane & 7) == 0) atomicAdd(&s.wg[lane == 0 ? DecP::OFF_BD : DecP::OFF_BC + (lane >> 3) - 1], t4);
                 }
             }
         }
@@ -268,6 +337,13 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? 2 : 3) k_render_train_p(Tra
             if (p.depth) p.depth[gidx] = dep;
             p.image[3 * gidx] = cr; p.image[3 * gidx + 1] = cg; p.image[3 * gidx + 2] = cb;
             if (p.num_samples) p.num_samples[gidx] = (int32_t)ns;
+        }
+    }
+    if (WG) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < DecP::BLOB; i += kCtaThreads) {
+            const float v = s.wg[i];
+            if (v != 0.0f) atomicAdd(p.grad_blob + i, v);
         }
     }
 }
@@ -345,6 +421,7 @@ using namespace ssdnerf;
 extern "C" {
 
 static int train_launch(const ssdnerf_render_train_args* a, bool bwd, cudaStream_t stream) {
+    const bool wg = bwd && a && a->grad_decoder_blob;
     if (!a) return set_error_msg(SSDNERF_ERR_ARG, "render_train: args is NULL");
     if (a->num_scenes == 0 || a->rays_per_scene == 0) return 0;
     if (a->variant != SSDNERF_DEC_P && a->variant != SSDNERF_DEC_P_SIMT && a->variant != SSDNERF_DEC_P_MMA && a->variant != SSDNERF_DEC_P_MMA2)
@@ -366,6 +443,7 @@ static int train_launch(const ssdnerf_render_train_args* a, bool bwd, cudaStream
     p.min_near = a->min_near; p.T_thresh = a->T_thresh; p.max_steps = a->max_steps;
     p.weights_sum = a->weights_sum; p.depth = a->depth; p.image = a->image; p.num_samples = a->num_samples;
     p.grad_ws = a->grad_ws; p.grad_image = a->grad_image; p.grad_planes = a->grad_planes;
+    p.grad_blob = wg ? a->grad_decoder_blob : nullptr;
     p.counter = a->counter;
     SSDNERF_CUDA_OK(cudaMemsetAsync(a->counter, 0, 4, stream));
 
@@ -373,9 +451,9 @@ static int train_launch(const ssdnerf_render_train_args* a, bool bwd, cudaStream
     SSDNERF_CUDA_OK(cudaGetDevice(&dev));
     SSDNERF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = sizeof(SmemT);
-    auto kern = bwd ? k_render_train_p<true> : k_render_train_p<false>;
-    static DeviceOnce attr_set[2];
-    if (attr_set[bwd].first()) {
+    auto kern = wg ? k_render_train_p<true, true> : bwd ? k_render_train_p<true, false> : k_render_train_p<false, false>;
+    static DeviceOnce attr_set[3];
+    if (attr_set[wg ? 2 : bwd].first()) {
         SSDNERF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     int occ = 0;

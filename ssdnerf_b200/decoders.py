@@ -7,9 +7,9 @@ return_loss)` returning `dict(weights_sum, depth, image)` as per-scene lists in 
 `point_density_decode`, attributes `bound / min_near / max_steps / aabb`.
 
 eval mode (`self.training == False`): ONE fused launch sequence (csrc/render_fused.cu, csrc/render_tc.cu).
-train mode: frozen decoder of the shipped-config shape (guidance / code optimisation, diffusion_nerf.py:273) ->
-fused differentiable renderer (csrc/render_train.cu, gradient w.r.t. the code only); a trainable decoder (training,
-SURVEY.md §8 f2) raises.  `point_decode` / `point_density_decode` are one native launch (csrc/point_decode.cu).
+train mode: decoder of the shipped-config shape -> fused differentiable renderer (csrc/render_train.cu): gradient w.r.t. the
+code (guidance / code optimisation with a frozen decoder, diffusion_nerf.py:273) and, when the decoder is trainable (stage-1
+auto-decoder training, multiscene_nerf.py:159-252), w.r.t. its weights.  `point_decode` / `point_density_decode` are one native launch (csrc/point_decode.cu).
 """
 import torch
 import torch.nn as nn
@@ -22,10 +22,11 @@ from .shencoder import SHEncoder
 
 
 class _FusedTrainRender(torch.autograd.Function):
-    """march + decode + composite as ONE differentiable op (gradient w.r.t. `code` [B,3,6,H,W] only)."""
+    """march + decode + composite as ONE differentiable op: gradient w.r.t. `code` [B,3,6,H,W] and, when any of them requires
+    one, w.r.t. the decoder parameters (`params`, in renderer.DEC_P_PARAM_ORDER; `blob` is their packed copy)."""
 
     @staticmethod
-    def forward(ctx, code, rays_o, rays_d, bitfield, blob, noises, dt_gamma, cfg):
+    def forward(ctx, code, rays_o, rays_d, bitfield, blob, noises, dt_gamma, cfg, *params):
         planes = R.pack_planes(code, R.DEC_P)
         hw = tuple(code.shape[-2:])
         out = R.render_train_fwd(planes, hw, bitfield, blob, rays_o, rays_d, noises=noises, dt_gamma=dt_gamma, **cfg)
@@ -39,9 +40,12 @@ class _FusedTrainRender(torch.autograd.Function):
         planes, rays_o, rays_d, bitfield, blob, noises, dt_gamma, ws, image = ctx.saved_tensors
         if grad_image is None:
             grad_image = torch.zeros_like(image)
-        grad_code = R.render_train_bwd(planes, ctx.hw, bitfield, blob, rays_o, rays_d, ws, image, grad_ws, grad_image,
-                                       noises=noises, dt_gamma=dt_gamma, **ctx.cfg)
-        return grad_code, None, None, None, None, None, None, None
+        want = any(ctx.needs_input_grad[8:])
+        out = R.render_train_bwd(planes, ctx.hw, bitfield, blob, rays_o, rays_d, ws, image, grad_ws, grad_image,
+                                 noises=noises, dt_gamma=dt_gamma, want_decoder_grad=want, **ctx.cfg)
+        if not want:
+            return (out,) + (None,) * (7 + len(ctx.needs_input_grad[8:]))
+        return (out[0],) + (None,) * 7 + R.unpack_decoder_blob_grad(out[1])
 
 
 class VolumeRenderer(nn.Module):
@@ -228,8 +232,15 @@ class TriPlaneDecoder(VolumeRenderer):
         # eval mode returns per-scene lists (base_volume_renderer.py:90-123)
         return dict(weights_sum=list(out['weights_sum']), depth=list(out['depth']), image=list(out['image']))
 
+    def trainable_params(self):
+        """the decoder parameters in renderer.DEC_P_PARAM_ORDER when at least one of them wants a gradient, else ()"""
+        if not any(p.requires_grad for p in self.parameters()):
+            return ()
+        named = dict(self.named_parameters())
+        return tuple(named[k] for k in R.DEC_P_PARAM_ORDER)
+
     def _fused_train_ok(self, rays_o, code, grid_size):
-        if self.code_dropout is not None or any(p.requires_grad for p in self.parameters()):
+        if self.code_dropout is not None:
             return False
         if not isinstance(rays_o, torch.Tensor) and len({r.size(0) for r in rays_o}) != 1:
             return False
@@ -260,16 +271,16 @@ class TriPlaneDecoder(VolumeRenderer):
         cfg = dict(grid_size=int(grid_size), bound=float(self.bound), min_near=float(self.min_near), max_steps=int(self.max_steps),
                    T_thresh=float(T_thresh))
         ws, depth, image = _FusedTrainRender.apply(code, rays_o, rays_d, density_bitfield.reshape(num_scenes, -1).contiguous(),
-                                                   self.packed_blob(), noises, dtg, cfg)
+                                                   self.packed_blob(), noises, dtg, cfg, *self.trainable_params())
         return dict(weights_sum=ws, depth=depth, image=image)
 
     def _forward_train(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh):
-        """base_volume_renderer.py:59-77.  The train branch exists as ONE fused differentiable op for the frozen shipped-config decoder
-        (guidance, code optimisation: diffusion_nerf.py:273,358).  A trainable decoder needs decoder-weight gradients (training,
-        SURVEY.md §8 f2), which this build does not have: it fails loudly rather than falling back to a PyTorch composition.  The
+        """base_volume_renderer.py:59-77.  The train branch exists as ONE fused differentiable op for the shipped-config decoder:
+        gradient w.r.t. the code (guidance, code optimisation: diffusion_nerf.py:273,358) and, for a trainable decoder, w.r.t. its
+        weights (multiscene_nerf.py:203-207).  Other decoder shapes fail loudly rather than fall back to a PyTorch composition.  The
         reference's per-op kernels stay available one by one in `ssdnerf_b200.raymarching` (march_rays_train, composite_rays_train)."""
         if self._fused_train_ok(rays_o, code, grid_size):
             return self._forward_train_fused(rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma, perturb, T_thresh)
         raise NotImplementedError(
-            'TriPlaneDecoder train branch: only the frozen shipped-config decoder (3x6-channel triplanes, hidden 64, dir_net) with equal ray '
-            'counts per scene is built (fused differentiable renderer); decoder-weight gradients are SURVEY.md §8 f2')
+            'TriPlaneDecoder train branch: only the shipped-config decoder (3x6-channel triplanes, hidden 64, dir_net, no code_dropout) '
+            'with equal ray counts per scene is built (fused differentiable renderer)')

@@ -1,4 +1,4 @@
-"""`BaseNeRF` / `MultiSceneNeRF` / `DiffusionNeRF` -- the registered models of the reference's configs, inference side.
+"""`BaseNeRF` / `MultiSceneNeRF` / `DiffusionNeRF` -- the registered models of the reference's configs.
 
 Plugin surface of lib/models/autodecoders/{base_nerf,multiscene_nerf,diffusion_nerf}.py: constructor kwargs, the registered names,
 `val_step(data, viz_dir=, viz_dir_guide=, **kw) -> {log_vars, num_samples, pred_imgs}` with all four branches of
@@ -8,8 +8,9 @@ diffusion_nerf.py:406-469 (stored scenes / `guide` / `optim` / `guide_optim` / u
 
 HOW it runs differs: DDIM = one replayed CUDA graph (diffusion.py), occupancy grid = 2 launches per iteration (density.py), render and
 the render loss = fused kernels (renderer.py), guidance through the denoiser and the diffusion-prior gradient of `val_optim` = the
-hand-written UNet input-gradient pass (unet.py `_UNetInputGrad`).  Training (`train_step`: decoder / UNet weight gradients, scene
-caches, DDP) is SURVEY.md §8 f2 and raises.
+hand-written UNet input-gradient pass (unet.py `_UNetInputGrad`).  Stage-1 training (`MultiSceneNeRF.train_step`: latents + decoder,
+scene cache) runs on the fused differentiable renderer with decoder-weight gradients; `DiffusionNeRF.train_step` (UNet weight
+gradients) is SURVEY.md §8 f2 and raises.
 """
 import functools
 import math
@@ -24,6 +25,7 @@ from . import _lib as N
 from . import density as D
 from . import renderer as R
 from .registry import MODELS, MODULES, build_module
+from .scene_cache import SceneCache
 
 
 # --------------------------------------------------------------------------------------------------------------------- small modules
@@ -190,7 +192,7 @@ class _RenderMSELoss(torch.autograd.Function):
     mse_render_loss (which also leaves d/d image, d/d weights_sum), backward = render_train_bwd (+ RegLoss gradient)."""
 
     @staticmethod
-    def forward(ctx, code, rays_o, rays_d, target, bitfield, blob, noises, dt_gamma, cfg, bg_color, pix_coef, reg_weight):
+    def forward(ctx, code, rays_o, rays_d, target, bitfield, blob, noises, dt_gamma, cfg, bg_color, pix_coef, reg_weight, *params):
         planes = R.pack_planes(code, R.DEC_P)
         hw = tuple(code.shape[-2:])
         out = R.render_train_fwd(planes, hw, bitfield, blob, rays_o, rays_d, noises=noises, dt_gamma=dt_gamma, **cfg)
@@ -209,11 +211,16 @@ class _RenderMSELoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pix, g_reg, g_rgb):
         planes, rays_o, rays_d, bitfield, blob, noises, dt_gamma, ws, image, g_image, g_ws, code = ctx.saved_tensors
+        want = any(ctx.needs_input_grad[12:])
         grad = R.render_train_bwd(planes, ctx.hw, bitfield, blob, rays_o, rays_d, ws, image, g_ws, g_image, noises=noises,
-                                  dt_gamma=dt_gamma, **ctx.cfg)
+                                  dt_gamma=dt_gamma, want_decoder_grad=want, **ctx.cfg)
+        gparams = (None,) * len(ctx.needs_input_grad[12:])
+        if want:      # trainable decoder (multiscene_nerf.py:203-207): weight gradients from the same backward launch
+            grad, gblob = grad
+            gparams = tuple(g * g_pix for g in R.unpack_decoder_blob_grad(gblob))
         if code is not None:      # RegLoss(power=2): d/d code = 2 w code / numel, with its own upstream gradient
-            return (torch.addcmul(grad * g_pix, code, g_reg, value=2.0 * ctx.reg_weight / code.numel()),) + (None,) * 11
-        return (grad * g_pix,) + (None,) * 11
+            return (torch.addcmul(grad * g_pix, code, g_reg, value=2.0 * ctx.reg_weight / code.numel()),) + (None,) * 11 + gparams
+        return (grad * g_pix,) + (None,) * 11 + gparams
 
 
 # --------------------------------------------------------------------------------------------------------------------- BaseNeRF
@@ -390,7 +397,7 @@ class BaseNeRF(nn.Module):
             pixel_loss, reg_loss, out_rgbs = _RenderMSELoss.apply(
                 code, rays_o, rays_d, target_rgbs.reshape(num_scenes, -1, 3), density_bitfield.reshape(num_scenes, -1).contiguous(),
                 decoder.packed_blob(), noises, dtg, rcfg, float(self.bg_color), float(self.pixel_loss.loss_weight * scale * 3),
-                None if self.reg_loss is None else float(self.reg_loss.loss_weight))
+                None if self.reg_loss is None else float(self.reg_loss.loss_weight), *decoder.trainable_params())
             loss, loss_dict = pixel_loss, dict(pixel_loss=pixel_loss)
             if self.reg_loss is not None:
                 loss = loss + reg_loss
@@ -538,19 +545,141 @@ class BaseNeRF(nn.Module):
         self.init_code.lerp_(mean_code, self.mean_ema_momentum)
 
     def train_step(self, data, optimizer, running_status=None):
-        raise NotImplementedError('training is outside the accelerated hot paths (SURVEY.md §8 f2)')
+        raise NotImplementedError('BaseNeRF has no train_step (the reference defines it on MultiSceneNeRF / DiffusionNeRF)')
 
 
 # --------------------------------------------------------------------------------------------------------------------- MultiSceneNeRF
+def _dist_info():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def _average_grads_across_ranks(module):
+    """what the reference gets from wrapping the decoder in DistributedDataParallel (apis/train.py): the shared decoder's gradient
+    is the mean over ranks, one flat all-reduce; per-scene latents are rank-private and are not reduced."""
+    rank, ws = _dist_info()
+    if ws == 1:
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    torch.distributed.all_reduce(flat)
+    flat /= ws
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
 @MODELS.register_module()
 class MultiSceneNeRF(BaseNeRF):
-    """multiscene_nerf.py:32-252 -- stage-1 auto-decoder.  The scene-code cache (RAM / file writers) and `train_step` are training
-    machinery; construction, scene I/O, `inverse_code`, `render` and `val_step` work."""
+    """multiscene_nerf.py:32-252 -- stage-1 auto-decoder: per-scene latents + shared decoder, trained jointly by `train_step` on the
+    fused differentiable renderer (code AND decoder-weight gradients from one backward launch); `val_step` renders stored scenes or
+    fits codes to `cond_imgs`.  Scene state between visits lives in `scene_cache.SceneCache`."""
 
     def __init__(self, *args, cache_size=0, cache_16bit=False, num_file_writers=0, **kwargs):
         super().__init__(*args, **kwargs)
         self.cache_size, self.cache_16bit, self.num_file_writers = cache_size, cache_16bit, num_file_writers
-        self.cache, self.cache_loaded = None, False
+        rank, ws = _dist_info()
+        self.scene_cache = SceneCache(cache_size, rank, ws, half=cache_16bit, num_file_writers=num_file_writers)
+
+    # the reference exposes the raw dict / flag; keep them readable under the same names
+    @property
+    def cache(self):
+        return self.scene_cache.entries
+
+    @property
+    def cache_loaded(self):
+        return self.scene_cache.loaded
+
+    def load_cache(self, data):
+        """multiscene_nerf.py:74-134 -> (code_list_, code_optimizers, density_grid [B,G^3], density_bitfield [B,G^3/8])"""
+        device = next(self.parameters()).device
+        sc = self.scene_cache
+        if sc.entries is not None:
+            if not sc.loaded:
+                src = self.train_cfg.get('cache_load_from', None)
+                if src is not None:
+                    sc.load_dir(src)
+                sc.loaded = True
+            states = [sc.get(i) for i in data['scene_id']]
+        elif 'code' in data:
+            states = data['code']
+        else:
+            states = [None] * len(data['scene_id'])
+        code_list_, grids, bitfields = [], [], []
+        for st in states:
+            if st is None:
+                code_list_.append(self.get_init_code_(None, device))
+                grids.append(self.get_init_density_grid(None, device))
+                bitfields.append(self.get_init_density_bitfield(None, device))
+                continue
+            par = st['param']
+            if 'code_' in par:
+                code_ = par['code_'].to(device=device, dtype=torch.float32, non_blocking=True, copy=True)      # never alias the cache entry
+            else:      # only the activated code was stored: invert the activation (lossy at the clip range, as the reference warns)
+                code_ = self.code_activation.inverse(par['code'].to(device=device, dtype=torch.float32))
+            code_list_.append(code_.requires_grad_(True))
+            grids.append(par['density_grid'].to(device, non_blocking=True))
+            bitfields.append(par['density_bitfield'].to(device, non_blocking=True))
+        code_optimizers = self.build_optimizer(code_list_, self.train_cfg)
+        for opt, st in zip(code_optimizers, states):
+            if st is not None and st.get('optimizer') is not None:
+                opt.load_state_dict(st['optimizer'])          # casts the stored moments to the latent's device / dtype
+        return code_list_, code_optimizers, torch.stack(grids), torch.stack(bitfields)
+
+    def save_cache(self, code_list_, code_optimizers, density_grid, density_bitfield, scene_id, scene_name):
+        """multiscene_nerf.py:136-183"""
+        save_dir = self.train_cfg.get('save_dir', None)
+        if save_dir is not None:
+            os.makedirs(save_dir, exist_ok=True)
+        for ind, code_ in enumerate(code_list_):
+            self.scene_cache.put(scene_id[ind], scene_name[ind], code_.data, density_grid[ind], density_bitfield[ind],
+                                 code_optimizers[ind].state_dict(), save_dir=save_dir)
+
+    def train_step(self, data, optimizer, running_status=None):
+        """multiscene_nerf.py:185-252: optional extra code-only steps, then ONE joint step of the scene latents (their own
+        optimizers) and the decoder (`optimizer['decoder']`) on `n_decoder_rays` random rays per scene."""
+        N.require_cuda(data['cond_imgs'], data['cond_poses'], data['cond_intrinsics'])
+        code_list_, code_optimizers, density_grid, density_bitfield = self.load_cache(data)
+        cond_imgs, cond_intrinsics, cond_poses = data['cond_imgs'], data['cond_intrinsics'], data['cond_poses']
+        num_scenes, num_imgs, h, w, _ = cond_imgs.size()
+        cond_rays_o, cond_rays_d = R.get_cam_rays(cond_poses, cond_intrinsics, h, w)
+        dt_gamma = self.train_cfg.get('dt_gamma_scale', 0.0) / cond_intrinsics[..., :2].mean(dim=(-2, -1))
+
+        extra = self.train_cfg.get('extra_scene_step', 0)
+        if extra > 0:
+            cfg = dict(self.train_cfg, n_inverse_steps=extra)
+            self.inverse_code(self.decoder, cond_imgs, cond_rays_o, cond_rays_d, dt_gamma=dt_gamma, cfg=cfg, code_=code_list_,
+                              density_grid=density_grid, density_bitfield=density_bitfield, code_optimizer=code_optimizers)
+
+        for o in code_optimizers:
+            o.zero_grad()
+        optimizer['decoder'].zero_grad()
+        code = self.code_activation(torch.stack(code_list_, dim=0), update_stats=True)
+        self.update_extra_state(self.decoder, code, density_grid, density_bitfield, 0,
+                                density_thresh=self.train_cfg.get('density_thresh', 0.01))
+        loss, log_vars, out_rgbs, target_rgbs = self.loss_decoder(self.decoder, code, density_bitfield, cond_rays_o, cond_rays_d,
+                                                                  cond_imgs, dt_gamma, cfg=self.train_cfg)
+        loss.backward()
+        log_vars.update(loss=float(loss))
+        _average_grads_across_ranks(self.decoder)
+        optimizer['decoder'].step()
+        for o in code_optimizers:
+            o.step()
+
+        self.save_cache(code_list_, code_optimizers, density_grid, density_bitfield, data['scene_id'], data['scene_name'])
+
+        with torch.no_grad():
+            self.mean_ema_update(code)
+            mse = (out_rgbs.reshape(num_scenes, -1) - target_rgbs.reshape(num_scenes, -1)).square().mean(dim=1)
+            log_vars.update(train_psnr=float((-10 * torch.log10(mse.clamp_min(1e-12))).mean()),
+                            code_rms=float(code.square().flatten(1).mean().sqrt()))
+            if data.get('test_imgs', None) is not None:
+                log_vars.update(self.eval_and_viz(data, self.decoder, code, density_bitfield, cfg=self.train_cfg)[0])
+        return dict(log_vars=log_vars, num_samples=num_scenes)
 
     def val_step(self, data, viz_dir=None, show_pbar=False, **kwargs):
         """multiscene_nerf.py:185-252: stored scenes are rendered; otherwise the codes are fitted to `cond_imgs` by inverse rendering"""
@@ -609,6 +738,12 @@ class DiffusionNeRF(MultiSceneNeRF):
             self.train_cfg_backup[key] = rgetattr(self, key)
 
     # ------------------------------------------------------------------ code <-> diffusion layout (diffusion_nerf.py:50-64)
+    def train_step(self, data, optimizer, running_status=None):
+        """diffusion_nerf.py:236-404 (single-stage training of denoiser + decoder + latents) needs UNet WEIGHT gradients; this build
+        has the UNet input-gradient pass only.  Stage-1 training is `MultiSceneNeRF.train_step`."""
+        raise NotImplementedError('DiffusionNeRF.train_step: denoiser weight gradients are not built (SURVEY.md §8 f2); '
+                                  'MultiSceneNeRF.train_step (stage 1) is')
+
     def code_diff_pr(self, code):
         """scene code [B, *code_size] -> the denoiser's layout: optional axis permutation (batch axis kept), then reshape"""
         out = code if self.code_permute is None else code.permute(0, *(a + 1 for a in self.code_permute))

@@ -43,22 +43,25 @@ def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cu
     `DecP` and csrc/render_tc.cu `DecS`)."""
     if variant is None:
         variant = detect_variant(params)
-    p = {k: v.detach().float().cpu() for k, v in params.items()}
+    p = {k: v.detach().float() for k, v in params.items()}       # packed where the weights live: no host round trip per optimiser step
+    src = p['base_net.0.weight'].device
+
+    def pad(t, n):
+        return torch.cat([t, torch.zeros(n, device=src)])
+    tail = torch.tensor([sigmoid_saturation, 0, 0, 0], dtype=torch.float32, device=src)
     if variant in (DEC_P, DEC_P_SIMT, DEC_P_TC, DEC_P_MMA, DEC_P_MMA2):
         w1 = _plane_major(p['base_net.0.weight'], 6).t().contiguous()           # [18][64], row k = plane*6+c
         parts = [w1.reshape(-1), p['base_net.0.bias'],
-                 p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),
+                 p['density_net.0.weight'].reshape(-1), pad(p['density_net.0.bias'], 3),
                  p['dir_net.0.weight'].t().contiguous().reshape(-1), p['dir_net.0.bias'],      # [16][64]
-                 p['color_net.0.weight'].reshape(-1), torch.cat([p['color_net.0.bias'], torch.zeros(1)]),
-                 torch.tensor([sigmoid_saturation, 0, 0, 0])]
+                 p['color_net.0.weight'].reshape(-1), pad(p['color_net.0.bias'], 1), tail]
     elif variant in (DEC_S, DEC_S_MMA, DEC_S_TC):
         w1 = _plane_major(p['base_net.0.weight'], 32)                             # [128][96] (N x K, K contiguous)
         wc0 = p['color_net.0.weight']                                             # [128][144]: cols 0..127 base_act, 128..143 SH
         parts = [w1.reshape(-1), p['base_net.0.bias'],
-                 p['density_net.0.weight'].reshape(-1), torch.cat([p['density_net.0.bias'], torch.zeros(3)]),
+                 p['density_net.0.weight'].reshape(-1), pad(p['density_net.0.bias'], 3),
                  wc0.reshape(-1), p['color_net.0.bias'],
-                 p['color_net.2.weight'].reshape(-1), torch.cat([p['color_net.2.bias'], torch.zeros(1)]),
-                 torch.tensor([sigmoid_saturation, 0, 0, 0])]
+                 p['color_net.2.weight'].reshape(-1), pad(p['color_net.2.bias'], 1), tail]
     else:
         raise N.SSDNeRFNativeError(f'unknown decoder variant {variant}')
     blob = torch.cat([x.float() for x in parts]).contiguous()
@@ -66,6 +69,28 @@ def pack_decoder_blob(params, variant=None, sigmoid_saturation=0.001, device='cu
     if blob.numel() != expect:
         raise N.SSDNeRFNativeError(f'decoder blob has {blob.numel()} floats, library expects {expect}')
     return blob.to(device)
+
+
+DEC_P_PARAM_ORDER = ('base_net.0.weight', 'base_net.0.bias', 'density_net.0.weight', 'density_net.0.bias',
+                     'dir_net.0.weight', 'dir_net.0.bias', 'color_net.0.weight', 'color_net.0.bias')
+
+
+def unpack_decoder_blob_grad(grad_blob):
+    """adjoint of `pack_decoder_blob` (variant P): blob-layout gradient [2572] -> tuple of parameter gradients in DEC_P_PARAM_ORDER"""
+    g = grad_blob
+    H, KF = 64, 18
+    o = 0
+    w1 = g[o:o + KF * H].reshape(3, 6, H); o += KF * H                     # [plane][c][out]
+    b1 = g[o:o + H]; o += H
+    wd = g[o:o + H].reshape(1, H); o += H
+    bd = g[o:o + 1]; o += 4
+    wdir = g[o:o + 16 * H].reshape(16, H); o += 16 * H
+    bdir = g[o:o + H]; o += H
+    wc = g[o:o + 3 * H].reshape(3, H); o += 3 * H
+    bc = g[o:o + 3]
+    # reference feature order of base_net's input is c*3 + plane (triplane_decoder.py:135-141)
+    return (w1.permute(2, 1, 0).reshape(H, KF).contiguous(), b1.clone(), wd.clone(), bd.clone(),
+            wdir.t().contiguous(), bdir.clone(), wc.clone(), bc.clone())
 
 
 def pack_planes(code, variant):
@@ -175,9 +200,11 @@ def render_train_fwd(planes, plane_hw, bitfield, blob, rays_o, rays_d, noises=No
 
 
 def render_train_bwd(planes, plane_hw, bitfield, blob, rays_o, rays_d, weights_sum, image, grad_ws, grad_image, noises=None,
-                     dt_gamma=None, grid_size=64, bound=1.0, min_near=0.2, max_steps=256, T_thresh=1e-4, code=None, reg_coef=0.0):
+                     dt_gamma=None, grid_size=64, bound=1.0, min_near=0.2, max_steps=256, T_thresh=1e-4, code=None, reg_coef=0.0,
+                     want_decoder_grad=False):
     """Train-branch backward: d(loss)/d(code) [B,3,6,H,W] from d(loss)/d(image) [B,N,3] and d(loss)/d(weights_sum) [B,N]
-    (+ reg_coef * code when `code` is given: the RegLoss(power=2) gradient of BaseNeRF.loss)."""
+    (+ reg_coef * code when `code` is given: the RegLoss(power=2) gradient of BaseNeRF.loss).
+    want_decoder_grad: also return d(loss)/d(decoder weights) in blob layout (-> `unpack_decoder_blob_grad`)."""
     import ctypes
     N.require_cuda(planes, bitfield, blob, rays_o, rays_d, weights_sum, image, grad_image)
     dev = planes.device
@@ -196,12 +223,16 @@ def render_train_bwd(planes, plane_hw, bitfield, blob, rays_o, rays_d, weights_s
     a.weights_sum, a.image = N.ptr(weights_sum), N.ptr(image)
     a.grad_ws, a.grad_image, a.grad_planes = N.ptr(grad_ws), N.ptr(grad_image), N.ptr(gplanes)
     a.counter = N.ptr(counter)
+    grad_blob = torch.zeros(blob.numel(), dtype=torch.float32, device=dev) if want_decoder_grad else None
+    a.grad_decoder_blob = N.ptr(grad_blob)
     N.check(N.lib().ssdnerf_render_train_bwd(ctypes.byref(a), N.stream_ptr()))
     grad_code = torch.empty(B, 3, 6, H, W, dtype=torch.float32, device=dev)
     if code is not None:
         code = code.contiguous().float()
     N.check(N.lib().ssdnerf_unpack_plane_grads(N.ptr(gplanes), N.ptr(code), N.c_f32(reg_coef), N.c_u32(B), N.c_u32(H), N.c_u32(W),
                                                N.c_int(0), N.ptr(grad_code), N.stream_ptr()))
+    if want_decoder_grad:
+        return grad_code, grad_blob
     return grad_code
 
 

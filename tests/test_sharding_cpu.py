@@ -31,7 +31,17 @@ def _worker(rank, world, port, num_scenes, q):
     lo, hi = view_range(V)
     local = torch.arange(lo, hi, dtype=torch.uint8)[:, None].repeat(1, 3) + bits[0, 0]
     views = gather_views(local, V)
-    q.put((rank, idx, full[:, 0, 0].tolist(), float(t), code[0].tolist(), views[:, 0].tolist()))
+    # stage-1 training: the shared decoder's gradient is averaged over ranks (the reference's DDP wrapper), scene-cache ownership
+    # follows the reference's linspace split
+    from ssdnerf_b200.nerf import _average_grads_across_ranks
+    from ssdnerf_b200.scene_cache import SceneCache
+    lin = torch.nn.Linear(3, 2)
+    lin.weight.grad = torch.full((2, 3), float(rank + 1))
+    lin.bias.grad = torch.tensor([10.0 * rank, 1.0])
+    _average_grads_across_ranks(lin)
+    owned = sorted(SceneCache(5, rank, world).entries)
+    q.put((rank, idx, full[:, 0, 0].tolist(), float(t), code[0].tolist(), views[:, 0].tolist(),
+           (lin.weight.grad.unique().tolist(), lin.bias.grad.tolist(), owned)))
     dist.destroy_process_group()
 
 
@@ -52,7 +62,9 @@ def test_world_size_2_gloo_gather():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, idx, full, tmax, code, views in res:
+    for rank, idx, full, tmax, code, views, train in res:
+        assert train[0] == [1.5] and train[1] == [5.0, 1.0]
+        assert train[2] == ([0, 1] if rank == 0 else [2, 3, 4])        # np.round(np.linspace(0, 5, 3)) = [0, 2, 5]
         assert full == [0.0, 1.0, 2.0, 3.0, 4.0] and tmax == 11.0
         assert idx == list(range(rank, 5, 2))
         assert code == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and views == [7 + v for v in range(7)]
