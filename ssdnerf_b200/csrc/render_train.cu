@@ -49,7 +49,7 @@ struct SmemT {
     float bd, bc[3], sat;
     float4 w1t[DecP::HID][5];               // backward only: W1 transposed, [o][k] padded to 20
     float hid[DecP::HID][kCtaThreads];      // backward only: base_x pre-activations of this thread's sample
-    float wg[DecP::BLOB];                   // weight-gradient kernel only: per-CTA partial sums in blob layout
+    float wg[kWarpsPerCta][DecP::BLOB];     // weight-gradient kernel only: per-WARP partial sums in blob layout (no shared atomics)
 };
 
 // Sum N per-lane values across the warp with N-1 + log2(32/N) shuffles (recursive halving): on return lane l holds the
@@ -105,7 +105,7 @@ __device__ __forceinline__ void scatter_plane_p(float* __restrict__ gplane, uint
 
 // WG (implies BWD): additionally accumulate d(loss)/d(decoder weights) -- the reference obtains these from autograd over the
 // materialised per-sample activations (base_volume_renderer.py:59-77 + triplane_decoder.py:119-179); here each warp reduces the
-// 2572 outer-product terms of its 32 samples with recursive-halving shuffles into a per-CTA shared-memory copy of the blob.
+// 2572 outer-product terms of its 32 samples with recursive-halving shuffles into a per-warp shared-memory copy of the blob.
 template <bool BWD, bool WG>
 __global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_train_p(TrainParams p) {
     static_assert(BWD || !WG, "weight gradients are part of the backward pass");
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_
                 w1t[i] = k < DecP::KF ? __ldg(blob + DecP::OFF_W1 + k * DecP::HID + o) : 0.0f;
             }
         }
-        if (WG) for (int i = threadIdx.x; i < DecP::BLOB; i += kCtaThreads) s.wg[i] = 0.0f;
+        if (WG) for (int i = threadIdx.x; i < kWarpsPerCta * DecP::BLOB; i += kCtaThreads) (&s.wg[0][0])[i] = 0.0f;
         if (threadIdx.x == 0) {
             s.bd = __ldg(blob + DecP::OFF_BD);
             s.bc[0] = __ldg(blob + DecP::OFF_BC); s.bc[1] = __ldg(blob + DecP::OFF_BC + 1); s.bc[2] = __ldg(blob + DecP::OFF_BC + 2);
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_
     __syncthreads();
 
     const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    float* const wgw = s.wg[threadIdx.x >> 5];
     const uint32_t tiles_per_scene = div_up(p.rays_per_scene, 32u);
     const uint32_t total_tiles = tiles_per_scene * p.num_scenes;
     const size_t plane_stride = (size_t)p.plane_h * p.plane_w * DecP::CPAD;
@@ -307,14 +308,17 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_
                         const float t32 = warp_reduce_scatter<32>(v32, lane);      // lane l: term l
                         const float t8 = warp_reduce_scatter<8>(v8, lane);         // lane l: term l >> 2
                         const int i32 = lane < DecP::KF ? DecP::OFF_W1 + lane * DecP::HID : DecP::OFF_WDIR + (lane - DecP::KF) * DecP::HID;
-                        atomicAdd(&s.wg[i32 + o], t32);
+                        // plain read-modify-write: within a warp every term has exactly one owner lane, and the copy is per warp.
+                        // (A shared-memory float atomicAdd is a CAS spin loop; lanes leaving it at different times broke the
+                        //  convergence the shuffles of the next hidden unit rely on.)
+                        wgw[i32 + o] += t32;
                         if ((lane & 3) == 0) {
                             const int q = lane >> 2;
                             const int i8 = q < 2 ? DecP::OFF_WDIR + (14 + q) * DecP::HID
                                          : q == 2 ? DecP::OFF_WD
                                          : q < 6 ? DecP::OFF_WC + (q - 3) * DecP::HID
                                          : q == 6 ? DecP::OFF_B1 : DecP::OFF_BDIR;
-                            atomicAdd(&s.wg[i8 + o], t8);
+                            wgw[i8 + o] += t8;
                         }
                     }
                 }
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_
                 if (WG) {                                              // head biases: bd, bc[0..2]
                     float v4[4] = {gsd, gp0, gp1, gp2};
                     const float t4 = warp_reduce_scatter<4>(v4, lane);  // lane l: term l >> 3
-                    if ((lane & 7) == 0) atomicAdd(&s.wg[lane == 0 ? DecP::OFF_BD : DecP::OFF_BC + (lane >> 3) - 1], t4);
+                    if ((lane & 7) == 0) wgw[lane == 0 ? DecP::OFF_BD : DecP::OFF_BC + (lane >> 3) - 1] += t4;
                 }
             }
         }
@@ -342,7 +346,9 @@ __global__ void __launch_bounds__(kCtaThreads, BWD ? (WG ? 1 : 2) : 3) k_render_
     if (WG) {
         __syncthreads();
         for (int i = threadIdx.x; i < DecP::BLOB; i += kCtaThreads) {
-            const float v = s.wg[i];
+            float v = 0.0f;
+#pragma unroll
+            for (int wi = 0; wi < kWarpsPerCta; ++wi) v += s.wg[wi][i];
             if (v != 0.0f) atomicAdd(p.grad_blob + i, v);
         }
     }

@@ -126,11 +126,13 @@ class TVLoss(nn.Module):
         self.dims, self.power, self.loss_weight = list(dims), power, loss_weight
 
     def forward(self, tensor, weight=None, avg_factor=None):
-        sq = 0
+        diffs = []
         for dim in self.dims:
             d = torch.diff(tensor, dim=dim)
-            sq = sq + torch.nn.functional.pad(d, [0, 0] * ((-dim - 1) % tensor.dim()) + [0, 1]).square()
-        loss = sq.sqrt().pow(self.power)
+            diffs.append(torch.nn.functional.pad(d, [0, 0] * ((-dim - 1) % tensor.dim()) + [0, 1]))
+        # vector_norm, not sqrt(sum of squares): its backward is 0 (not 0 * inf) where all differences vanish, e.g. the all-zero
+        # latents every scene starts from under init_from_mean
+        loss = torch.linalg.vector_norm(torch.stack(diffs), dim=0).pow(self.power)
         if weight is not None:
             loss = loss * weight
         loss = loss.mean() if avg_factor is None else loss.sum() / avg_factor
@@ -426,7 +428,7 @@ class BaseNeRF(nn.Module):
         out_rgbs, loss, loss_dict = self.loss(decoder, code, density_bitfield, target_rgbs, rays_o, rays_d, dt_gamma, return_decoder_loss=True,
                                               scale_num_ray=cond_rays_o.shape[1:4].numel(), cfg=cfg, **kwargs)
         decoder.train(prev)
-        return loss, {k: float(v) for k, v in loss_dict.items()}, out_rgbs, target_rgbs
+        return loss, {k: float(v.detach()) for k, v in loss_dict.items()}, out_rgbs, target_rgbs
 
     # ------------------------------------------------------------------ occupancy grid (base_nerf.py:318-401)
     def update_extra_state(self, decoder, code, density_grid, density_bitfield, iter_density, density_thresh=0.01, decay=0.9,
@@ -664,7 +666,7 @@ class MultiSceneNeRF(BaseNeRF):
         loss, log_vars, out_rgbs, target_rgbs = self.loss_decoder(self.decoder, code, density_bitfield, cond_rays_o, cond_rays_d,
                                                                   cond_imgs, dt_gamma, cfg=self.train_cfg)
         loss.backward()
-        log_vars.update(loss=float(loss))
+        log_vars.update(loss=float(loss.detach()))
         _average_grads_across_ranks(self.decoder)
         optimizer['decoder'].step()
         for o in code_optimizers:
