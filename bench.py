@@ -331,18 +331,24 @@ def run_ours(args):
         Sh.gather_views((img[0].clamp(0, 1) * 255.0 + 0.5).to(torch.uint8), V, out=ss_all, padded=ss_u8)
     strong_ms = timed(strong_step, 10, 3)
 
+    # ---- stage-1 training step (every rank trains its own scenes; the shared decoder's gradient is all-reduced over NCCL inside the step)
+    train = None
+    if args.train:
+        train = train_measurement(dev, timed, rank)
+
     # ---- config-4 shape guided evaluations (rank 0): UNet forward + render loss forward/backward + UNet input-gradient pass
     guided = None
     if args.guided and rank == 0:
         guided = guided_measurement(dev, ev, stream)
 
     # ---- reduce over ranks (max time)
-    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms or 0.0, strong_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms or 0.0, strong_ms, train['ms'] if train else 0.0], device=dev,
+                         dtype=torch.float64)
     sums = torch.tensor([samples, s_samples or 0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms_all, strong_ms = [float(x) for x in times.tolist()]
+    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms_all, strong_ms, train_ms = [float(x) for x in times.tolist()]
     samples_all, s_samples_all = [float(x) for x in sums.tolist()]
     if rank != 0:
         if world > 1:
@@ -403,11 +409,51 @@ def run_ours(args):
                          'frac': (s_samples_all / world * 768 + rays * RAY_IO_BYTES) / (s_ms_all * 1e-3) / 1e9 / pk['hbm_gbs']}}
     if guided is not None:
         line['guided'] = guided
+    if train is not None:
+        line['train_stage1'] = dict(train['info'], n_gpus=world, ms_per_train_step=train_ms,
+                                    scenes_per_sec=train['scenes'] * world / (train_ms * 1e-3),
+                                    rays_fwd_bwd_per_sec=train['rays_per_step'] * world / (train_ms * 1e-3), scaling='weak')
     if args.cpu_baseline and world == 1:          # reported baseline: rank 0 at N = 1 only
         line['cpu_baseline'] = cpu_reference_sample(quick=True)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_measurement(dev, timed, rank, views=16, steps=4):
+    """`stage1_cars_recons16v` (reference config, resolved) at its own sizes: samples_per_gpu scenes x 16 views 128x128 per rank,
+    `extra_scene_step` code-only Adam steps + ONE joint step of latents and decoder (weight gradients from the fused backward, gradient
+    all-reduce over NCCL at N > 1) per train_step, 4096 rays per scene per step, scene cache write-back included."""
+    import ssdnerf_b200 as S
+    cfg = reference_config('configs/paper_cfgs/stage1_cars_recons16v.py')
+    train_cfg = {k: v for k, v in cfg['train_cfg'].items() if k != 'cache_load_from'}
+    torch.manual_seed(0)                                   # same initial decoder on every rank (the reference broadcasts it through DDP)
+    scenes = cfg['samples_per_gpu']
+    model = S.build_model(dict(cfg['model'], cache_size=0), train_cfg=train_cfg, test_cfg=cfg['test_cfg']).to(dev).train()
+    model.scene_cache = S.scene_cache.SceneCache(scenes, 0, 1)      # every rank caches its own `scenes` scenes
+    g = torch.Generator().manual_seed(100 + rank)
+    poses = orbit_poses(views)[None].repeat(scenes, 1, 1, 1).contiguous().to(dev)
+    intr = torch.tensor([131.25, 131.25, 64.0, 64.0]).expand(scenes, views, 4).contiguous().to(dev)
+    code = (torch.randn(scenes, 3, 6, 128, 128, generator=g) * 0.5).to(dev)
+    with torch.no_grad():
+        _, bits = model.get_density(model.decoder, code, cfg=dict(density_thresh=0.1))
+        imgs, _ = model.render(model.decoder, code, bits, IMG, IMG, intr, poses, cfg=dict(dt_gamma_scale=0.5))
+    data = dict(scene_id=list(range(scenes)), scene_name=[f'r{rank}s{i}' for i in range(scenes)], cond_imgs=imgs.clamp(0, 1), cond_poses=poses,
+                cond_intrinsics=intr)
+    opt = dict(decoder=torch.optim.Adam(model.decoder.parameters(), lr=1e-3))
+    log = {}
+
+    def step():
+        log.update(model.train_step(data, opt)['log_vars'])
+    ms = timed(step, steps, 3)
+    inner = train_cfg['extra_scene_step'] + 1
+    rays = scenes * (train_cfg['extra_scene_step'] * train_cfg['n_inverse_rays'] + train_cfg['n_decoder_rays'])
+    if not all(v == v for v in log.values()):
+        raise RuntimeError(f'stage-1 training step produced non-finite values: {log}')
+    return dict(ms=ms, scenes=scenes, rays_per_step=rays,
+                info={'workload': f'stage1_cars_recons16v (reference config): {scenes} scenes x {views} views {IMG}x{IMG} per GPU, {inner} optimiser '
+                                  f'steps per train_step ({train_cfg["extra_scene_step"]} code-only + 1 joint with decoder-weight gradients), '
+                                  f'{train_cfg["n_decoder_rays"]} rays/scene/step', 'last_log_vars': log})
 
 
 def guided_measurement(dev, ev, stream, scenes=8, evals=6):
@@ -525,6 +571,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     ap.add_argument('--no-side-s', dest='side_s', action='store_false', help='skip the variant-S renderer workload')
     ap.add_argument('--no-guided', dest='guided', action='store_false', help='skip the config-4 guided-evaluation measurement')
+    ap.add_argument('--no-train', dest='train', action='store_false', help='skip the stage-1 training-step measurement')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3      # timing rule: at least 3 warm-up steps

@@ -9,10 +9,10 @@ Everything computes through libssdnerf_b200.so (C ABI: include/ssdnerf_b200.h); 
 """
 from .registry import MODELS, MODULES, build_model, build_module  # noqa: F401
 from .config import Config  # noqa: F401
-from . import activation, decoders, density, diffusion, nerf, raymarching, renderer, shencoder, unet  # noqa: F401
+from . import activation, decoders, density, diffusion, nerf, raymarching, renderer, scene_cache, shencoder, unet  # noqa: F401
 from .decoders import TriPlaneDecoder  # noqa: F401
 from .diffusion import GaussianDiffusion  # noqa: F401
-from .nerf import DiffusionNeRF  # noqa: F401
+from .nerf import DiffusionNeRF, MultiSceneNeRF  # noqa: F401
 from .unet import DenoisingUnetMod  # noqa: F401
 
 __version__ = '0.1.0'
