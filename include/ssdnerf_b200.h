@@ -352,6 +352,8 @@ typedef struct ssdnerf_gn_bwd_args {
     const void* add;                       /* optional gradient added to the result (shortcut / residual), fp16 [B][HW][C1+C2] */
     float* group_sums;                     /* scratch [B][groups][2] */
     void* dx1; void* dx2;                  /* out: fp16 [B][HW][C1], [B][HW][C2] */
+    float* channel_sums;                   /* optional out [B][C1+C2][2]: sum_p dy', sum_p dy' * xhat with dy' = d loss / d (xhat*g' + b')
+                                              (after the SiLU derivative): d gamma, d beta, d scale, d shift are linear in them */
 } ssdnerf_gn_bwd_args;
 SSDNERF_API int ssdnerf_gn_bwd(const ssdnerf_gn_bwd_args* args, void* stream);
 /* dS = P * (dP - rowsum(P * dP)): softmax backward over attention rows; P fp16, dP fp32, dS fp16, [rows][T] */
@@ -372,6 +374,33 @@ SSDNERF_API int ssdnerf_grad_nchw_to_nhwc_f16(const float* g, uint32_t B, uint32
                                               void* out, void* stream);
 SSDNERF_API int ssdnerf_grad_nhwc_to_nchw_f32(const float* dx, uint32_t B, uint32_t C, uint32_t H, uint32_t W, uint32_t Cpad, const float* scale,
                                               float* out, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * 4c. Weight gradients of the UNet's convolutions / linear layers (training of the denoiser).
+ *     replaces: autograd of mmgen's conv / linear modules under lib/models/autodecoders/diffusion_nerf.py:113-121
+ *               (loss_diffusion.backward(); optimizer['diffusion'].step())
+ *     dw[co][tap][dw_c0 + ci] += sum over (b, y, x) of gy[b][y][x][gy_c0 + co] * X[b][y*stride + dy - 1][x*stride + dx - 1][x_c0 + ci]
+ *     (tap = (dy+1)*3 + (dx+1); taps == 1: no offset / padding; up: X is read through a nearest x2 upsample).  fp16 operands
+ *     (mma.sync tensor cores, tiles transposed by ldmatrix.trans), fp32 accumulation, split over the pixel axis; dw is ACCUMULATED.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ssdnerf_wgrad_args {
+    const void* gy; uint32_t gy_stride, gy_c0;     /* fp16 [batch*out_h*out_w][gy_stride] */
+    const void* x; uint32_t x_stride, x_c0;        /* fp16 [batch][in_h][in_w][x_stride] */
+    float* dw; uint32_t dw_stride, dw_c0;          /* fp32 [cout][taps][dw_stride] */
+    uint32_t batch, out_h, out_w, in_h, in_w;
+    uint32_t cout, cin;                            /* multiples of 64 */
+    uint32_t taps;                                 /* 1 or 9 */
+    uint32_t stride;                               /* 1 or 2 */
+    int up;                                        /* 1: input is nearest-upsampled x2 before the convolution */
+    uint32_t ksplit;                               /* 0 = choose */
+} ssdnerf_wgrad_args;
+SSDNERF_API int ssdnerf_conv_wgrad_f16(const ssdnerf_wgrad_args* args, void* stream);
+/* out[c] += sum_r src[r][c0 + c]   (bias gradients); src fp16 [rows][stride], channels % 8 == 0 */
+/* in-place inverted dropout on fp16 data with a counter-based mask (same seed -> same mask: the backward re-applies it to the gradient);
+ * replaces nn.Dropout of DenoisingResBlock (mmgen, used by lib/models/architecture/diffusion/modules.py:51-110) in training */
+SSDNERF_API int ssdnerf_dropout_f16(void* x, unsigned long long n, unsigned long long seed, float p_drop, void* stream);
+SSDNERF_API int ssdnerf_colsum_f16(const void* src, uint64_t rows, uint32_t stride, uint32_t c0, uint32_t channels, float* out, void* stream);
 
 #ifdef __cplusplus
 }

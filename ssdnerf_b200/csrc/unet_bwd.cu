@@ -37,6 +37,7 @@ struct GnBwdParams {
     const __half* dy;                                          // gradient w.r.t. the normalised (+SiLU) output, [B][HW][C1+C2]
     const __half* add;                                         // optional gradient added to the result, [B][HW][C1+C2]
     float* gsum;                                               // [B][groups][2]: sum dxh, sum dxh * xhat
+    float* csum;                                               // optional [B][C1+C2][2]: per-channel sum dy', sum dy' * xhat (weight-gradient pass)
     __half* dx1; __half* dx2;                                  // outputs, [B][HW][C1] and [B][HW][C2]
 };
 
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd(const GnBwdParams p) {
             s_gm[threadIdx.x] = make_float2(t.x * inv_n, t.y * inv_n);
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.0f;
+        for (uint32_t i = threadIdx.x; i < (p.csum ? 4 : 2) * C; i += blockDim.x) s_acc[i] = 0.0f;
     }
     __syncthreads();
     float m1[8], m2[8], a1[8], a2[8];
@@ -128,15 +129,23 @@ __global__ void __launch_bounds__(256) k_gn_bwd(const GnBwdParams p) {
                 const float r = rs[k] * (dxh - m1[k] - xh * m2[k]);
                 o[k] = add ? o[k] + r : r;
             } else {
-                a1[k] += dxh; a2[k] = fmaf(dxh, xh, a2[k]);
+                a1[k] += d; a2[k] = fmaf(d, xh, a2[k]);            // w.r.t. y = xhat * gp + bp; the group sums want these times gp
             }
         }
         if (APPLY) *reinterpret_cast<uint4*>(dst + (size_t)pix * cs) = bf_to_h8(o);
     }
     if (!APPLY) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[v * 8 + k], a1[k]); atomicAdd(&s_acc[C + v * 8 + k], a2[k]); }
+        for (int k = 0; k < 8; ++k) {
+            atomicAdd(&s_acc[v * 8 + k], a1[k] * gp[k]); atomicAdd(&s_acc[C + v * 8 + k], a2[k] * gp[k]);
+            if (p.csum) { atomicAdd(&s_acc[2 * C + v * 8 + k], a1[k]); atomicAdd(&s_acc[3 * C + v * 8 + k], a2[k]); }
+        }
         __syncthreads();
+        if (p.csum)      // d gamma / d beta / d scale / d shift are linear in these two sums per (image, channel)
+            for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
+                atomicAdd(p.csum + ((size_t)b * C + c) * 2, s_acc[2 * C + c]);
+                atomicAdd(p.csum + ((size_t)b * C + c) * 2 + 1, s_acc[3 * C + c]);
+            }
         for (uint32_t g = threadIdx.x; g < p.groups; g += blockDim.x) {
             float s = 0.0f, q = 0.0f;
             for (uint32_t c = g * cpg; c < (g + 1) * cpg; ++c) { s += s_acc[c]; q += s_acc[C + c]; }
@@ -324,6 +333,8 @@ int ssdnerf_gn_bwd(const ssdnerf_gn_bwd_args* a, void* stream) {
     p.stats = a->stats; p.stats2 = a->stats2; p.quad_stats = a->quad_stats; p.gamma = a->gamma; p.beta = a->beta;
     p.scale_shift = a->scale_shift; p.ss_batch_stride = a->ss_batch_stride; p.eps = a->eps; p.do_silu = a->do_silu;
     p.dy = (const __half*)a->dy; p.add = (const __half*)a->add; p.gsum = a->group_sums; p.dx1 = (__half*)a->dx1; p.dx2 = (__half*)a->dx2;
+    p.csum = a->channel_sums;
+    if (p.csum) SSDNERF_CUDA_OK(cudaMemsetAsync(p.csum, 0, (size_t)a->B * C * 2 * sizeof(float), s));
     const uint32_t cv = C / 8, threads = cv * (256 / cv);
     uint32_t chunks = (a->HW + 7) / 8;
     const uint32_t max_chunks = (148 * 8 + a->B - 1) / a->B;
@@ -331,7 +342,7 @@ int ssdnerf_gn_bwd(const ssdnerf_gn_bwd_args* a, void* stream) {
     p.pix_per_block = (a->HW + chunks - 1) / chunks;
     chunks = (a->HW + p.pix_per_block - 1) / p.pix_per_block;
     SSDNERF_CUDA_OK(cudaMemsetAsync(a->group_sums, 0, (size_t)a->B * a->groups * 2 * sizeof(float), s));
-    k_gn_bwd<false><<<dim3(chunks, a->B), threads, 2 * C * sizeof(float), s>>>(p);
+    k_gn_bwd<false><<<dim3(chunks, a->B), threads, (p.csum ? 4 : 2) * C * sizeof(float), s>>>(p);
     SSDNERF_LAUNCH_OK();
     k_gn_bwd<true><<<dim3(chunks, a->B), threads, 0, s>>>(p);
     SSDNERF_LAUNCH_OK();

@@ -344,11 +344,14 @@ class GnBwdArgs(ctypes.Structure):
         ('stats', N.c_void_p), ('stats2', N.c_void_p), ('quad_stats', N.c_int), ('gamma', N.c_void_p), ('beta', N.c_void_p),
         ('scale_shift', N.c_void_p), ('ss_batch_stride', c_ll), ('eps', N.c_f32), ('do_silu', N.c_int),
         ('dy', N.c_void_p), ('add', N.c_void_p), ('group_sums', N.c_void_p), ('dx1', N.c_void_p), ('dx2', N.c_void_p),
+        ('channel_sums', N.c_void_p),
     ]
 
 
-def gn_bwd(x1, x2, stats, gamma, beta, dy, dx1, dx2=None, add=None, scale_shift_ptr=None, ss_batch_stride=0, silu=True, gsum=None, eps=1e-5):
-    """GroupNorm(32)(+scale/shift)(+SiLU) backward over the channel concat of x1 (+x2); stats = (quad_flag, s1, s2) as the forward used."""
+def gn_bwd(x1, x2, stats, gamma, beta, dy, dx1, dx2=None, add=None, scale_shift_ptr=None, ss_batch_stride=0, silu=True, gsum=None, eps=1e-5,
+           csum=None):
+    """GroupNorm(32)(+scale/shift)(+SiLU) backward over the channel concat of x1 (+x2); stats = (quad_flag, s1, s2) as the forward used.
+    csum (fp32 [B, C, 2], overwritten): per-(image, channel) sums the affine / scale-shift parameter gradients are built from."""
     N.require_cuda(x1, dy, dx1)
     B, H, W, C1 = x1.shape
     a = GnBwdArgs()
@@ -370,8 +373,46 @@ def gn_bwd(x1, x2, stats, gamma, beta, dy, dx1, dx2=None, add=None, scale_shift_
     a.group_sums = gsum.data_ptr()
     a.dx1 = dx1.data_ptr()
     a.dx2 = dx2.data_ptr() if dx2 is not None else None
+    a.channel_sums = csum.data_ptr() if csum is not None else None
     N.check(N.lib().ssdnerf_gn_bwd(ctypes.byref(a), N.stream_ptr()))
     return dx1, dx2
+
+
+class WgradArgs(ctypes.Structure):
+    """mirror of `ssdnerf_wgrad_args`"""
+    _fields_ = [
+        ('gy', N.c_void_p), ('gy_stride', N.c_u32), ('gy_c0', N.c_u32),
+        ('x', N.c_void_p), ('x_stride', N.c_u32), ('x_c0', N.c_u32),
+        ('dw', N.c_void_p), ('dw_stride', N.c_u32), ('dw_c0', N.c_u32),
+        ('batch', N.c_u32), ('out_h', N.c_u32), ('out_w', N.c_u32), ('in_h', N.c_u32), ('in_w', N.c_u32),
+        ('cout', N.c_u32), ('cin', N.c_u32), ('taps', N.c_u32), ('stride', N.c_u32), ('up', N.c_int), ('ksplit', N.c_u32),
+    ]
+
+
+def conv_wgrad(gy, x, dw, cout, cin, taps=1, stride=1, up=False, gy_c0=0, x_c0=0, dw_c0=0, ksplit=0):
+    """dw[co, tap, dw_c0 + ci] += sum_pixels gy[..., gy_c0 + co] * x[shifted pixel, x_c0 + ci]  (header section 4c).
+    gy fp16 [B,Ho,Wo,Cg]; x fp16 [B,Hi,Wi,Cx]; dw fp32 [cout, taps, K] contiguous."""
+    N.require_cuda(gy, x, dw)
+    assert gy.dtype == torch.float16 and x.dtype == torch.float16 and dw.dtype == torch.float32 and dw.is_contiguous()
+    B, Ho, Wo, Cg = gy.shape
+    _, Hi, Wi, Cx = x.shape
+    a = WgradArgs()
+    a.gy, a.gy_stride, a.gy_c0 = gy.data_ptr(), Cg, gy_c0
+    a.x, a.x_stride, a.x_c0 = x.data_ptr(), Cx, x_c0
+    a.dw, a.dw_stride, a.dw_c0 = dw.data_ptr(), dw.shape[-1], dw_c0
+    a.batch, a.out_h, a.out_w, a.in_h, a.in_w = B, Ho, Wo, Hi, Wi
+    a.cout, a.cin, a.taps, a.stride, a.up, a.ksplit = cout, cin, taps, stride, int(up), ksplit
+    N.check(N.lib().ssdnerf_conv_wgrad_f16(ctypes.byref(a), N.stream_ptr()))
+    return dw
+
+
+def colsum(src, channels, out, c0=0):
+    """out[c] += sum over rows of src[..., c0 + c]; src fp16 [..., stride] contiguous, out fp32 [channels]"""
+    N.require_cuda(src, out)
+    stride = src.shape[-1]
+    N.check(N.lib().ssdnerf_colsum_f16(N.ptr(src), c_u64(src.numel() // stride), N.c_u32(stride), N.c_u32(c0), N.c_u32(channels),
+                                       N.ptr(out), N.stream_ptr()))
+    return out
 
 
 def transpose_f16(src_ptr, dst, rows, cols, row_stride, stride1, n1, stride2, n2):
@@ -426,3 +467,14 @@ def attn_backward(qkv, d_o, heads, scale, ws):
     _bgemm(dSt.data_ptr(), a_tt, T, qt.data_ptr(), b_ct, ch, T, heads, B, dp + ch * 2, o_str, False, scale)        # dk = scale dS^T q
     _bgemm(Pt.data_ptr(), a_tt, T, dot.data_ptr(), b_ct, ch, T, heads, B, dp + 2 * ch * 2, o_str, False, 1.0)      # dv = P^T d_o
     return dqkv
+
+
+def dropout_f16(x, seed, p):
+    """in-place inverted dropout with the mask a pure function of (seed, element index)"""
+    if p <= 0:
+        return x
+    N.require_cuda(x)
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    N.check(N.lib().ssdnerf_dropout_f16(N.ptr(x), ctypes.c_ulonglong(x.numel()), ctypes.c_ulonglong(seed & (2 ** 64 - 1)), N.c_f32(p),
+                                        N.stream_ptr()))
+    return x
