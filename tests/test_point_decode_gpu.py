@@ -52,9 +52,16 @@ def test_point_decode_refuses_gradients_and_trainable_decoder(cuda):
     dec.requires_grad_(True)
     with pytest.raises(NotImplementedError):
         dec.point_decode(x, [x[0]], code.detach())
-    # trainable decoder: the train branch fails loudly (no PyTorch composition in the product)
+    # trainable decoder: the train branch is the fused differentiable renderer with decoder-weight gradients (no PyTorch composition)
+    out = dec(torch.zeros(1, 8, 3, device=cuda), torch.ones(1, 8, 3, device=cuda), code.detach(),
+              torch.zeros(1, 64 ** 3 // 8, dtype=torch.uint8, device=cuda), 64)
+    assert out['image'].requires_grad and out['image'].shape == (1, 8, 3)
+    # other decoder shapes have no differentiable kernel: they fail loudly
+    import ssdnerf_b200 as S
+    dec_s = S.build_module(dict(type='TriPlaneDecoder')).to(cuda).train()
     with pytest.raises(NotImplementedError):
-        dec(torch.zeros(1, 8, 3, device=cuda), torch.ones(1, 8, 3, device=cuda), code.detach(), torch.zeros(1, 64 ** 3 // 8, dtype=torch.uint8, device=cuda), 64)
+        dec_s(torch.zeros(1, 8, 3, device=cuda), torch.ones(1, 8, 3, device=cuda), torch.zeros(1, 3, 32, 128, 128, device=cuda),
+              torch.zeros(1, 64 ** 3 // 8, dtype=torch.uint8, device=cuda), 64)
 
 
 def test_extract_fields_matches_oracle(cuda):
