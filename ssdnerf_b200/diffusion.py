@@ -470,12 +470,10 @@ class GaussianDiffusion(nn.Module):
         return self.ddpm_loss(loss_kwargs)
 
     def forward_train(self, x_0, concat_cond=None, grad_guide_fn=None, cfg=dict(), x_t_detach=False, t=None, noise=None, **kwargs):
-        """gaussian_diffusion.py:423-450: diffusion loss of x_0 at sampled timesteps.  Differentiable w.r.t. x_0 (the UNet weights are
-        frozen constants in this build: test-time code optimisation; UNet training is SURVEY.md §8 f2).  `t` / `noise` may be injected."""
+        """gaussian_diffusion.py:423-450: diffusion loss of x_0 at sampled timesteps.  Differentiable w.r.t. x_0 (test-time code
+        optimisation with a frozen denoiser: input-gradient pass) and, when the denoiser's parameters require gradients (training),
+        w.r.t. them as well (unet_train.py weight-gradient pass).  `t` / `noise` may be injected."""
         assert x_0.dim() == 4
-        if any(p.requires_grad for p in self.denoising.parameters()):
-            raise NotImplementedError('training the denoiser needs UNet weight gradients (SURVEY.md §8 f2); freeze it '
-                                      '(module_requires_grad(diffusion, False)) to differentiate w.r.t. the latent only')
         num_batches = x_0.size(0)
         if t is None:
             t = self.sampler(num_batches)

@@ -9,8 +9,8 @@ diffusion_nerf.py:406-469 (stored scenes / `guide` / `optim` / `guide_optim` / u
 HOW it runs differs: DDIM = one replayed CUDA graph (diffusion.py), occupancy grid = 2 launches per iteration (density.py), render and
 the render loss = fused kernels (renderer.py), guidance through the denoiser and the diffusion-prior gradient of `val_optim` = the
 hand-written UNet input-gradient pass (unet.py `_UNetInputGrad`).  Stage-1 training (`MultiSceneNeRF.train_step`: latents + decoder,
-scene cache) runs on the fused differentiable renderer with decoder-weight gradients; `DiffusionNeRF.train_step` (UNet weight
-gradients) is SURVEY.md §8 f2 and raises.
+scene cache) runs on the fused differentiable renderer with decoder-weight gradients; `DiffusionNeRF.train_step` (single-stage / stage-2
+training) adds the denoiser's weight-gradient pass (unet_train.py, csrc/wgrad.cu).
 """
 import functools
 import math
@@ -283,7 +283,7 @@ class BaseNeRF(nn.Module):
             if load_density:
                 grids.append(param['density_grid'])
                 bits.append(param['density_bitfield'])
-        code = torch.stack(codes, dim=0).to(device)
+        code = torch.stack(codes, dim=0).to(device=device, dtype=torch.float32)
         if not load_density:
             return code, None, None
         return code, torch.stack(grids, dim=0).to(device), torch.stack(bits, dim=0).to(device)
@@ -741,10 +741,82 @@ class DiffusionNeRF(MultiSceneNeRF):
 
     # ------------------------------------------------------------------ code <-> diffusion layout (diffusion_nerf.py:50-64)
     def train_step(self, data, optimizer, running_status=None):
-        """diffusion_nerf.py:236-404 (single-stage training of denoiser + decoder + latents) needs UNet WEIGHT gradients; this build
-        has the UNet input-gradient pass only.  Stage-1 training is `MultiSceneNeRF.train_step`."""
-        raise NotImplementedError('DiffusionNeRF.train_step: denoiser weight gradients are not built (SURVEY.md §8 f2); '
-                                  'MultiSceneNeRF.train_step (stage 1) is')
+        """diffusion_nerf.py:66-189.  One iteration of single-stage training (latents + decoder + denoiser), of stage 2 (denoiser on
+        stored scenes: no `optimizer` entry in train_cfg, `code` in data) or of any mix the config's optimizers select:
+        diffusion loss -> denoiser step (UNet weight gradients: unet_train.py) with the prior gradient landing on the latents ->
+        `extra_scene_step` render-loss Adam steps that START from that prior gradient -> joint render step of latents / decoder ->
+        cache write-back.  `optimizer`: dict with keys 'diffusion*' and optionally 'decoder' (the reference's runner builds it)."""
+        diffusion = self.diffusion
+        decoder = self.decoder_ema if self.freeze_decoder and self.decoder_use_ema else self.decoder
+        num_scenes = len(data['scene_id'])
+        extra_scene_step = self.train_cfg.get('extra_scene_step', 0)
+        if 'optimizer' in self.train_cfg:
+            code_list_, code_optimizers, density_grid, density_bitfield = self.load_cache(data)
+            code = self.code_activation(torch.stack(code_list_, dim=0), update_stats=True)
+        else:
+            assert 'code' in data
+            code, density_grid, density_bitfield = self.load_scene(data, load_density='decoder' in optimizer)
+            code_list_, code_optimizers = [], []
+        diffusion_opts = [v for k, v in optimizer.items() if k.startswith('diffusion')]
+        for o in diffusion_opts + code_optimizers:
+            o.zero_grad()
+        if 'decoder' in optimizer:
+            optimizer['decoder'].zero_grad()
+
+        has_views = 'cond_imgs' in data
+        if has_views:
+            cond_imgs, cond_intrinsics, cond_poses = data['cond_imgs'], data['cond_intrinsics'], data['cond_poses']
+            num_scenes, num_imgs, h, w, _ = cond_imgs.size()
+            cond_rays_o, cond_rays_d = R.get_cam_rays(cond_poses, cond_intrinsics, h, w)
+            dt_gamma = self.train_cfg.get('dt_gamma_scale', 0.0) / cond_intrinsics[..., :2].mean(dim=(-2, -1))
+            if self.image_cond:
+                raise NotImplementedError('image_cond training (concat_cond) is unused by every shipped config and not built')
+
+        loss_diffusion, log_vars = diffusion(self.code_diff_pr(code), concat_cond=None, return_loss=True,
+                                             x_t_detach=self.train_cfg.get('x_t_detach', False), cfg=self.train_cfg)
+        loss_diffusion.backward()
+        _average_grads_across_ranks(diffusion)
+        for o in diffusion_opts:
+            o.step()
+
+        prior_grad = None
+        if extra_scene_step > 0:
+            assert len(code_optimizers) > 0
+            prior_grad = [c.grad.detach().clone() for c in code_list_]
+            cfg = dict(self.train_cfg, n_inverse_steps=extra_scene_step)
+            code, _, _, _, loss_dict_decoder, _, _ = self.inverse_code(
+                decoder, cond_imgs, cond_rays_o, cond_rays_d, dt_gamma=dt_gamma, cfg=cfg, code_=code_list_, density_grid=density_grid,
+                density_bitfield=density_bitfield, code_optimizer=code_optimizers, prior_grad=prior_grad)
+            log_vars.update({k: float(v) for k, v in loss_dict_decoder.items()})
+
+        if 'decoder' in optimizer or len(code_optimizers) > 0:
+            if len(code_optimizers) > 0:
+                code = self.code_activation(torch.stack(code_list_, dim=0))
+            self.update_extra_state(decoder, code, density_grid, density_bitfield, 0, density_thresh=self.train_cfg.get('density_thresh', 0.01))
+            loss_decoder, log_vars_decoder, out_rgbs, target_rgbs = self.loss_decoder(
+                decoder, code, density_bitfield, cond_rays_o, cond_rays_d, cond_imgs, dt_gamma, cfg=self.train_cfg)
+            log_vars.update(log_vars_decoder)
+            if prior_grad is not None:
+                for c, g in zip(code_list_, prior_grad):
+                    c.grad.copy_(g)
+            loss_decoder.backward()
+            if 'decoder' in optimizer:
+                _average_grads_across_ranks(decoder)
+                optimizer['decoder'].step()
+            for o in code_optimizers:
+                o.step()
+            if len(code_optimizers) > 0:
+                self.save_cache(code_list_, code_optimizers, density_grid, density_bitfield, data['scene_id'], data['scene_name'])
+            with torch.no_grad():
+                if len(code_optimizers) > 0:
+                    self.mean_ema_update(code)
+                mse = (out_rgbs.reshape(num_scenes, -1) - target_rgbs.reshape(num_scenes, -1)).square().mean(dim=1)
+                log_vars.update(train_psnr=float((-10 * torch.log10(mse.clamp_min(1e-12))).mean()),
+                                code_rms=float(code.square().flatten(1).mean().sqrt()))
+                if data.get('test_imgs', None) is not None:
+                    log_vars.update(self.eval_and_viz(data, self.decoder, code, density_bitfield, cfg=self.train_cfg)[0])
+            log_vars.update(loss_decoder=float(loss_decoder.detach()))
+        return dict(log_vars=log_vars, num_samples=num_scenes)
 
     def code_diff_pr(self, code):
         """scene code [B, *code_size] -> the denoiser's layout: optional axis permutation (batch axis kept), then reshape"""

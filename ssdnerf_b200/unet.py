@@ -128,6 +128,7 @@ class DenoisingUnetMod(nn.Module):
         self.channel_factor_list = list(channels_cfg)
         self.num_heads = num_heads
         self.base_channels = base_channels
+        self.dropout = float(dropout)
         emb_ch = base_channels * 4 if embedding_channels == -1 else embedding_channels
         self.embedding_channels = emb_ch
         self.time_embedding = _TimeEmbedding(base_channels, emb_ch)
@@ -178,7 +179,10 @@ class DenoisingUnetMod(nn.Module):
         device = device or next(self.parameters()).device
         key = (batch, str(device), tuple(p._version for p in self.parameters()))
         if self._engine is None or self._engine_key != key:
+            old = self._engine
             self._engine = UNetEngine(self, batch, device)
+            if old is not None and self._engine_key is not None and self._engine_key[:2] == key[:2]:
+                self._engine.bufs = old.bufs          # only the weights changed (optimizer step): keep the activation / scratch arena
             self._engine_key = key
         return self._engine
 
@@ -207,6 +211,10 @@ class DenoisingUnetMod(nn.Module):
         B = h.shape[0]
         if t.dim() == 0 or t.numel() != B:
             t = t.expand(B)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training of the denoiser: input-gradient + weight-gradient pass (unet_train.py)
+            from .unet_train import forward_with_weight_grads
+            return forward_with_weight_grads(self, h, t)
         if torch.is_grad_enabled() and h.requires_grad:
             if self.concat_cond_channels > 0:
                 raise NotImplementedError('input gradients with concat_cond are not built (unused by the shipped configs)')
@@ -272,7 +280,7 @@ class UNetEngine:
                      g2=f32(p.norm_with_embedding.norm.weight), b2=f32(p.norm_with_embedding.norm.bias),
                      w2=U.pack_conv_weight(p.conv_2[-1].weight).to(dev), c2b=f32(p.conv_2[-1].bias),
                      emb_w=f32(p.norm_with_embedding.embedding_layer[1].weight), emb_b=f32(p.norm_with_embedding.embedding_layer[1].bias),
-                     n1=self._norm_slot(), n2=self._norm_slot(), idx=len(self.res_blocks))
+                     n1=self._norm_slot(), n2=self._norm_slot(), idx=len(self.res_blocks), mod=p)
             if hasattr(p, 'shortcut'):
                 d['ws'] = U.pack_linear_weight(p.shortcut.weight).to(dev)
                 d['wsb'] = f32(p.shortcut.bias)
@@ -282,15 +290,15 @@ class UNetEngine:
         def attn(p):
             return ('attn', dict(c=p.c, heads=p.num_heads, g=f32(p.norm.weight), b=f32(p.norm.bias),
                                  wqkv=U.pack_linear_weight(p.qkv.weight).to(dev), bqkv=f32(p.qkv.bias),
-                                 wproj=U.pack_linear_weight(p.proj.weight).to(dev), bproj=f32(p.proj.bias), n=self._norm_slot()))
+                                 wproj=U.pack_linear_weight(p.proj.weight).to(dev), bproj=f32(p.proj.bias), n=self._norm_slot(), mod=p))
 
         def layer(p):
             if isinstance(p, _ResBlockParams): return res(p)
             if isinstance(p, _AttnParams): return attn(p)
             if isinstance(p, _DownParams):
-                return ('down', dict(c=p.c, w=U.pack_conv_weight(p.downsample.weight).to(dev), b=f32(p.downsample.bias)))
+                return ('down', dict(c=p.c, w=U.pack_conv_weight(p.downsample.weight).to(dev), b=f32(p.downsample.bias), mod=p))
             if isinstance(p, _UpParams):
-                return ('up', dict(c=p.c, w=U.pack_upconv_weight(p.conv.weight).to(dev), b=f32(p.conv.bias)))
+                return ('up', dict(c=p.c, w=U.pack_upconv_weight(p.conv.weight).to(dev), b=f32(p.conv.bias), mod=p))
             raise TypeError(type(p))
 
         conv_in = m.in_blocks[0][0]
@@ -313,6 +321,7 @@ class UNetEngine:
         self.ss_total = off
         self.ss_cur = torch.zeros(batch, self.ss_total, dtype=torch.float32, device=dev)
         self.saving, self.tape, self.fwd_token, self._bwd_packed = False, [], 0, False
+        self.drop_p, self._drop_seed = float(m.dropout), None      # ResBlock dropout: active only in the training forward
         self.x_in = torch.zeros(batch, self.H, self.W, self.CPAD_IN, dtype=torch.float16, device=dev)
         self.v_out = torch.zeros(batch, self.H, self.W, self.out_conv['cout'], dtype=torch.float32, device=dev)
 
@@ -328,10 +337,22 @@ class UNetEngine:
         return t
 
     # ------------------------------------------------------------------ embeddings
-    def scale_shift_rows(self, emb):
-        """emb [R, emb_ch] -> [R, ss_total]: every ResBlock's Linear(SiLU(emb)) (NormWithEmbedding.embedding_layer)."""
+    def scale_shift_rows(self, emb, live=False):
+        """emb [R, emb_ch] -> [R, ss_total]: every ResBlock's Linear(SiLU(emb)) (NormWithEmbedding.embedding_layer).
+        live=True uses the module's parameters themselves (differentiable: the weight-gradient pass back-propagates through it)."""
         e = torch.nn.functional.silu(emb.float())
+        if live:
+            lins = [d['mod'].norm_with_embedding.embedding_layer[1] for d in self.res_blocks]
+            return torch.cat([torch.nn.functional.linear(e, l.weight.float(), l.bias.float()) for l in lins], dim=1)
         return torch.cat([torch.nn.functional.linear(e, d['emb_w'], d['emb_b']) for d in self.res_blocks], dim=1)
+
+    def new_dropout_seed(self, training):
+        """draw the dropout seed of the next save-mode forward from torch's CPU generator (None: dropout off)"""
+        self._drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and self.drop_p > 0) else None
+
+    def _dropout(self, a2, block_idx):
+        if self._drop_seed is not None:
+            U.dropout_f16(a2, self._drop_seed + 0x9E3779B97F4A7C15 * (block_idx + 1), self.drop_p)
 
     def set_embedding(self, emb):
         """per-sample time embedding [B, emb_ch] for the next forward"""
@@ -393,6 +414,7 @@ class UNetEngine:
             h1 = U.conv3x3_f16(a, d['w1'], cout, bias=d['c1b'], out=self._buf(('h1', tag), (B, H, W, cout)), qstats=qh1)
             a2 = self._gn(h1, qh1, None, None, d['g2'], d['b2'], self._buf(('a2', H, cout), (B, H, W, cout)), True, self.ss_offsets[d['idx']])
             st2 = self._last_stats
+            self._dropout(a2, d['idx'])
             out = U.conv3x3_f16(a2, d['w2'], cout, bias=d['c2b'], residual=sc, out=self._buf(('res_out', tag), (B, H, W, cout)), qstats=qo)
             self.tape.append(dict(kind='res', d=d, x=x, sk=sk, st1=st1, h1=h1, st2=st2, out=out, tag=tag))
             return out, qo
@@ -420,21 +442,27 @@ class UNetEngine:
         st = self._last_stats
         qkv = U.linear_f16(xn.view(B * T, c), d['wqkv'], bias=d['bqkv'], n=3 * c,
                            out=self._buf(('qkv', tag) if self.saving else ('qkv', T, c), (B * T, 3 * c)))
-        if self.flash_attention and ch in (64, 128) and T % 64 == 0:
-            o = U.flash_attn(qkv.view(B, T, 3 * c), heads, 1.0 / math.sqrt(ch), out=self._buf(('o', T, c), (B, T, c)))
-        else:   # unfused composition (scores -> softmax -> P V), kept for head widths / lengths the fused kernel does not cover
-            S = U.attn_scores(qkv.view(B, T, 3 * c), heads, scale=1.0 / math.sqrt(ch), out=self._buf(('S', T), (B, heads, T, T), torch.float32))
-            P = self._buf(('P', T), (B, heads, T, T))
-            N.check(L.ssdnerf_softmax_rows(N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(P), s))
-            vt = self._buf(('vt', T, c), (B, heads, ch, T))
-            N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
-            o = U.attn_pv(P, vt, out=self._buf(('o', T, c), (B, T, c)))
+        o = self._attn_core(qkv, B, T, c, heads, ('o', T, c))
         qo = self._q(('attn_out', tag), c)
         out = U.linear_f16(o.view(B * T, c), d['wproj'], bias=d['bproj'], residual=x.view(B * T, c), n=c,
                            out=self._buf(('attn_out', tag), (B * T, c)), qstats=qo, stats_hw=T).view(B, H, W, c)
         if self.saving:
             self.tape.append(dict(kind='attn', d=d, x=x, st=st, qkv=qkv.view(B, T, 3 * c), out=out, tag=tag))
         return out, qo
+
+    def _attn_core(self, qkv, B, T, c, heads, out_key):
+        """softmax(q k^T / sqrt(ch)) v on the qkv projection [B*T, 3c] (legacy head layout) -> [B, T, c]"""
+        ch = c // heads
+        L, s = N.lib(), N.stream_ptr()
+        if self.flash_attention and ch in (64, 128) and T % 64 == 0:
+            return U.flash_attn(qkv.view(B, T, 3 * c), heads, 1.0 / math.sqrt(ch), out=self._buf(out_key, (B, T, c)))
+        # unfused composition (scores -> softmax -> P V), kept for head widths / lengths the fused kernel does not cover
+        S = U.attn_scores(qkv.view(B, T, 3 * c), heads, scale=1.0 / math.sqrt(ch), out=self._buf(('S', T), (B, heads, T, T), torch.float32))
+        P = self._buf(('P', T), (B, heads, T, T))
+        N.check(L.ssdnerf_softmax_rows(N.ptr(S), N.c_u32(B * heads * T), N.c_u32(T), N.ptr(P), s))
+        vt = self._buf(('vt', T, c), (B, heads, ch, T))
+        N.check(L.ssdnerf_transpose_v(N.ptr(qkv), N.c_u32(B), N.c_u32(T), N.c_u32(heads), N.c_u32(ch), N.ptr(vt), s))
+        return U.attn_pv(P, vt, out=self._buf(out_key, (B, T, c)))
 
     def _down(self, d, x, tag):
         x, _ = x
@@ -529,8 +557,9 @@ class UNetEngine:
         self.out_conv['wT'] = U.pack_conv_weight_dgrad(m.out.conv.weight, cout_pad=self.CPAD_IN).to(dev)  # K = 18 -> 64, rows = 128
         self._bwd_packed = True
 
-    def backward_nchw(self, grad_v):
-        """grad_v fp32 [B,C,H,W] (d loss / d v) -> d loss / d x_t fp32 [B,C,H,W], for the forward that just ran with save=True."""
+    def backward_nchw(self, grad_v, wg=None):
+        """grad_v fp32 [B,C,H,W] (d loss / d v) -> d loss / d x_t fp32 [B,C,H,W], for the forward that just ran with save=True.
+        With a `unet_train.WeightGradPass` the same walk also produces the parameter gradients: returns (dx, grads, d_scale_shift)."""
         B, C, H, W = grad_v.shape
         L, s = N.lib(), N.stream_ptr()
         scale = self._buf(('bwd', 'scale'), (2,), torch.float32)
@@ -538,13 +567,16 @@ class UNetEngine:
         g_in = self._buf(('bwd', 'g_in'), (B, H, W, self.CPAD_IN))
         N.check(L.ssdnerf_grad_nchw_to_nhwc_f16(N.ptr(grad_v), N.c_u32(B), N.c_u32(C), N.c_u32(H), N.c_u32(W), N.c_u32(self.CPAD_IN),
                                                 N.ptr(scale), N.ptr(g_in), s))
-        dx = self.backward_nhwc(g_in)
+        dx = self.backward_nhwc(g_in, wg=wg)
         out = torch.empty(B, self.cin_total, H, W, dtype=torch.float32, device=self.dev)
         N.check(L.ssdnerf_grad_nhwc_to_nchw_f32(N.ptr(dx), N.c_u32(B), N.c_u32(self.cin_total), N.c_u32(H), N.c_u32(W), N.c_u32(self.CPAD_IN),
                                                 N.ptr(scale), N.ptr(out), s))
+        if wg is not None:
+            grads, d_ss = wg.finish(scale[1])
+            return out, grads, d_ss
         return out
 
-    def backward_nhwc(self, g_v):
+    def backward_nhwc(self, g_v, wg=None):
         """g_v fp16 [B,H,W,CPAD_IN] (loss-scaled d loss / d v, zero beyond the model's channels) -> fp32 [B,H,W,CPAD_IN] d loss / d x_in.
         Walks the tape of the last save=True forward in reverse; every convolution / linear gradient is the forward's tensor-core
         kernel on transposed weights, the rest are the section-4b glue kernels."""
@@ -576,7 +608,10 @@ class UNetEngine:
                 B, H, W, c = x.shape
                 d_a = U.conv3x3_f16(g_v, self.out_conv['wT'], c, out=gb('d_a', (H, c), (B, H, W, c)))
                 dh = gb('dx', idx, (B, H, W, c))
-                U.gn_bwd(x, None, r['st'], self.out_norm['g'], self.out_norm['b'], d_a, dh, silu=True, gsum=gsum)
+                cs = wg.csum(c) if wg else None
+                U.gn_bwd(x, None, r['st'], self.out_norm['g'], self.out_norm['b'], d_a, dh, silu=True, gsum=gsum, csum=cs)
+                if wg:
+                    wg.out(r, g_v, cs)
                 acc(x, dh)
             elif kind == 'res':
                 d, x, sk, h1, out = r['d'], r['x'], r['sk'], r['h1'], r['out']
@@ -585,9 +620,14 @@ class UNetEngine:
                 C2 = sk.shape[-1] if sk is not None else 0
                 cin, cout = d['cin'], d['cout']
                 d_a2 = U.conv3x3_f16(g, d['w2T'], cout, out=gb('d_a2', (H, cout), (B, H, W, cout)))
+                self._dropout(d_a2, d['idx'])                     # same mask as the forward (a no-op outside training)
                 d_h1 = gb('d_h1', (H, cout), (B, H, W, cout))
                 ss = N.c_void_p(self.ss_cur.data_ptr() + 4 * self.ss_offsets[d['idx']])
-                U.gn_bwd(h1, None, r['st2'], d['g2'], d['b2'], d_a2, d_h1, scale_shift_ptr=ss, ss_batch_stride=self.ss_total, silu=True, gsum=gsum)
+                cs2 = wg.csum(cout) if wg else None
+                U.gn_bwd(h1, None, r['st2'], d['g2'], d['b2'], d_a2, d_h1, scale_shift_ptr=ss, ss_batch_stride=self.ss_total, silu=True, gsum=gsum,
+                         csum=cs2)
+                if wg:      # conv_2 / norm 2 / embedding rows now: cs2 and the 'a' scratch are reused below
+                    wg.res_second(r, g, cs2)
                 d_a = U.conv3x3_f16(d_h1, d['w1T'], cin, out=gb('d_a', (H, cin), (B, H, W, cin)))
                 if 'wsT' in d:
                     add = U.conv3x3_f16(g, d['wsT'].unsqueeze(0), cin, taps=1, out=gb('d_sc', (H, cin), (B, H, W, cin)))
@@ -596,7 +636,10 @@ class UNetEngine:
                     add = g
                 dx = gb('dx', idx, (B, H, W, C1))
                 dsk = gb('dsk', idx, (B, H, W, C2)) if sk is not None else None
-                U.gn_bwd(x, sk, r['st1'], d['g1'], d['b1'], d_a, dx, dsk, add=add, silu=True, gsum=gsum)
+                cs1 = wg.csum(cin) if wg else None
+                U.gn_bwd(x, sk, r['st1'], d['g1'], d['b1'], d_a, dx, dsk, add=add, silu=True, gsum=gsum, csum=cs1)
+                if wg:
+                    wg.res_first(r, g, d_h1, cs1)
                 acc(x, dx)
                 if sk is not None:
                     acc(sk, dsk)
@@ -610,12 +653,17 @@ class UNetEngine:
                                        lambda name, shape, dtype: gb('att_' + name, (T, c), shape, dtype))
                 d_xn = U.linear_f16(dqkv.view(B * T, 3 * c), d['wqkvT'], n=c, out=gb('d_xn', (T, c), (B * T, c)))
                 dx = gb('dx', idx, (B, H, W, c))
-                U.gn_bwd(x, None, r['st'], d['g'], d['b'], d_xn.view(B, H, W, c), dx, add=g, silu=False, gsum=gsum)
+                cs = wg.csum(c) if wg else None
+                U.gn_bwd(x, None, r['st'], d['g'], d['b'], d_xn.view(B, H, W, c), dx, add=g, silu=False, gsum=gsum, csum=cs)
+                if wg:
+                    wg.attn(r, g, dqkv, cs)
                 acc(x, dx)
             elif kind == 'down':
                 d, x, out = r['d'], r['x'], r['out']
                 g = grads.pop(out.data_ptr())
                 B, H, W, c = x.shape
+                if wg:
+                    wg.down(r, g)
                 M = B * (H // 2) * (W // 2)
                 dcol = U.linear_f16(g.view(M, c), d['wT'], n=9 * c, out=gb('dcol', (H, c), (M, 9 * c)))
                 dx = gb('dx', idx, (B, H, W, c))
@@ -626,12 +674,16 @@ class UNetEngine:
                 d, x, out = r['d'], r['x'], r['out']
                 g = grads.pop(out.data_ptr())
                 B, H, W, c = x.shape
+                if wg:
+                    wg.up(r, g)
                 dup = U.conv3x3_f16(g, d['wT'], c, out=gb('dup', (H, c), (B, 2 * H, 2 * W, c)))
                 dx = gb('dx', idx, (B, H, W, c))
                 N.check(L.ssdnerf_sum2x2(N.ptr(dup), N.c_u32(B), N.c_u32(H), N.c_u32(W), N.c_u32(c), N.ptr(dx), s()))
                 acc(x, dx)
             elif kind == 'conv_in':
                 g = grads.pop(r['out'].data_ptr())
+                if wg:
+                    wg.conv_in(r, g)
                 dx_in = self._buf(('bwd', 'dx_in'), (self.B, self.H, self.W, self.CPAD_IN), torch.float32)
                 U.conv3x3_f16(g, self.conv_in['wT'], self.cin_total, out=dx_in)
         assert not grads, 'dangling gradients in the UNet tape'

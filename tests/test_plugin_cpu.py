@@ -121,8 +121,13 @@ def test_ddim_tables_match_oracle():
 def test_unsupported_paths_fail_loudly():
     cfg = S.Config.fromfile(os.path.join(ROOT, 'configs', 'cars_uncond_b200.py'))
     m = S.build_model(cfg.model, test_cfg=cfg.test_cfg)
-    with pytest.raises(NotImplementedError):
-        m.train_step({}, None)
+    # training runs on the native kernels only: CPU tensors are refused, never routed to a PyTorch fallback
+    stored = [dict(param=dict(code=torch.zeros(3, 6, 128, 128), density_grid=torch.zeros(64 ** 3).half(),
+                              density_bitfield=torch.zeros(64 ** 3 // 8, dtype=torch.uint8)))]
+    m.train_cfg = dict()
+    with pytest.raises(S._lib.SSDNeRFNativeError):
+        m.train().train_step(dict(scene_id=[0], scene_name=['a'], code=stored), dict(diffusion=torch.optim.SGD(m.diffusion.parameters(), lr=0.1)))
+    m.eval()
     with pytest.raises(S._lib.SSDNeRFNativeError):
         m.render(m.decoder, torch.zeros(1, 3, 6, 128, 128), torch.zeros(1, 32768, dtype=torch.uint8), 8, 8,
                  torch.zeros(1, 1, 4), torch.zeros(1, 1, 4, 4))

@@ -107,3 +107,65 @@ def test_stage1_16bit_cache_and_scene_files(cuda, tmp_path):
     assert torch.equal(bits[0].cpu(), rec['param']['density_bitfield'])
     out = m2.train_step(data, dict(decoder=torch.optim.Adam(m2.decoder.parameters(), lr=1e-3)))
     assert out['log_vars']['loss'] == out['log_vars']['loss']
+
+
+def _diffusion_model(cuda, name, cache_size=0, **train_over):
+    import ssdnerf_b200 as S
+    c = json.load(open(os.path.join(GOLDEN, 'reference_configs.json')))[name]
+    train_cfg = {k: v for k, v in c['train_cfg'].items() if k != 'cache_load_from'}
+    train_cfg.update(train_over)
+    torch.manual_seed(0)
+    model = S.build_model(dict(c['model'], cache_size=cache_size), train_cfg=train_cfg, test_cfg=c['test_cfg'])
+    g = torch.Generator().manual_seed(0)
+    for p in model.diffusion.denoising.parameters():          # mmgen zero-initialises the last conv of every block: give them values
+        if p.dim() > 1:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return model.to(cuda).train(), c
+
+
+def test_stage2_train_step_trains_the_denoiser(cuda):
+    """`stage2_cars_uncond` (reference config): stored scenes, only the diffusion optimizer; full-size UNet, 2 scenes"""
+    model, c = _diffusion_model(cuda, 'configs/paper_cfgs/stage2_cars_uncond.py')
+    assert 'optimizer' not in model.train_cfg and model.freeze_decoder
+    g = torch.Generator().manual_seed(1)
+    stored = [dict(param=dict(code=torch.tanh(torch.randn(3, 6, 128, 128, generator=g)) * 0.8, density_grid=torch.zeros(64 ** 3).half(),
+                              density_bitfield=torch.zeros(64 ** 3 // 8, dtype=torch.uint8))) for _ in range(2)]
+    data = dict(scene_id=[0, 1], scene_name=['a', 'b'], code=stored)
+    unet = model.diffusion.denoising
+    w0 = {k: v.detach().clone() for k, v in unet.named_parameters()}
+    opt = dict(diffusion=torch.optim.Adam(model.diffusion.parameters(), lr=1e-4))
+    losses = []
+    for _ in range(3):
+        out = model.train_step(data, opt)
+        assert out['num_samples'] == 2 and 'loss_ddpm_mse' in out['log_vars']
+        losses.append(out['log_vars']['loss_ddpm_mse'])
+    assert all(v == v and v < 1e6 for v in losses), losses
+    missing = [k for k, p in unet.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all() or float(p.grad.abs().max()) == 0]
+    assert not missing, missing[:8]
+    assert all(not torch.equal(p.detach(), w0[k]) for k, p in unet.named_parameters())
+    assert all(p.grad is None for p in model.decoder.parameters())
+    # the EMA copy is not touched by train_step (the reference updates it from a runner hook)
+    assert model.diffusion_ema is not model.diffusion
+
+
+def test_single_stage_train_step(cuda):
+    """`ssdnerf_cars_uncond` (reference config): latents (scene cache) + decoder + denoiser in one iteration; fewer inner steps / rays"""
+    model, c = _diffusion_model(cuda, 'configs/paper_cfgs/ssdnerf_cars_uncond.py', cache_size=4, extra_scene_step=2, n_decoder_rays=1024,
+                                n_inverse_rays=1024)
+    assert not model.freeze_decoder and 'optimizer' in model.train_cfg
+    B, V, res = 2, 3, 64
+    imgs, poses, intr = _scenes(model, cuda, B, V, res, 3)
+    opt = dict(diffusion=torch.optim.Adam(model.diffusion.parameters(), lr=1e-4), decoder=torch.optim.Adam(model.decoder.parameters(), lr=1e-3))
+    data = dict(scene_id=[0, 3], scene_name=['s0', 's3'], cond_imgs=imgs, cond_poses=poses, cond_intrinsics=intr)
+    dec0 = {k: v.detach().clone() for k, v in model.decoder.named_parameters()}
+    unet0 = model.diffusion.denoising.in_blocks[0][0].weight.detach().clone()
+    for _ in range(2):
+        out = model.train_step(data, opt)
+    lv = out['log_vars']
+    assert set(lv) >= {'loss_ddpm_mse', 'pixel_loss', 'loss_decoder', 'train_psnr', 'code_rms'} and all(v == v for v in lv.values()), lv
+    assert all(not torch.equal(p.detach(), dec0[k]) for k, p in model.decoder.named_parameters())
+    assert not torch.equal(model.diffusion.denoising.in_blocks[0][0].weight.detach(), unet0)
+    e = model.cache[3]
+    assert e is not None and int(e['optimizer']['state'][0]['step']) == 2 * (2 + 1)
+    # the diffusion prior reached the latents: with x_t_detach unset the code receives a gradient from the diffusion loss
+    assert float(e['optimizer']['state'][0]['exp_avg'].abs().sum()) > 0
