@@ -332,9 +332,10 @@ def run_ours(args):
     strong_ms = timed(strong_step, 10, 3)
 
     # ---- stage-1 training step (every rank trains its own scenes; the shared decoder's gradient is all-reduced over NCCL inside the step)
-    train = None
+    train = train2 = None
     if args.train:
         train = train_measurement(dev, timed, rank)
+        train2 = train_stage2_measurement(dev, timed, rank)
 
     # ---- config-4 shape guided evaluations (rank 0): UNet forward + render loss forward/backward + UNet input-gradient pass
     guided = None
@@ -342,13 +343,13 @@ def run_ours(args):
         guided = guided_measurement(dev, ev, stream)
 
     # ---- reduce over ranks (max time)
-    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms or 0.0, strong_ms, train['ms'] if train else 0.0], device=dev,
-                         dtype=torch.float64)
+    times = torch.tensor([total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms or 0.0, strong_ms, train['ms'] if train else 0.0,
+                          train2['ms'] if train2 else 0.0], device=dev, dtype=torch.float64)
     sums = torch.tensor([samples, s_samples or 0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms_all, strong_ms, train_ms = [float(x) for x in times.tolist()]
+    total_ms, ddim_ms, dens_ms, rend_ms, e2e_ms, s_ms_all, strong_ms, train_ms, train2_ms = [float(x) for x in times.tolist()]
     samples_all, s_samples_all = [float(x) for x in sums.tolist()]
     if rank != 0:
         if world > 1:
@@ -413,6 +414,11 @@ def run_ours(args):
         line['train_stage1'] = dict(train['info'], n_gpus=world, ms_per_train_step=train_ms,
                                     scenes_per_sec=train['scenes'] * world / (train_ms * 1e-3),
                                     rays_fwd_bwd_per_sec=train['rays_per_step'] * world / (train_ms * 1e-3), scaling='weak')
+    if train2 is not None:
+        line['train_stage2'] = dict(train2['info'], n_gpus=world, ms_per_train_step=train2_ms,
+                                    triplanes_per_sec=train2['scenes'] * world / (train2_ms * 1e-3),
+                                    unet_fwd_bwd_wgrad_tflops_per_gpu=3 * UNET_FLOP_PER_SAMPLE_STEP * train2['scenes'] / (train2_ms * 1e-3) / 1e12,
+                                    scaling='weak')
     if args.cpu_baseline and world == 1:          # reported baseline: rank 0 at N = 1 only
         line['cpu_baseline'] = cpu_reference_sample(quick=True)
     print(json.dumps(line))
@@ -454,6 +460,37 @@ def train_measurement(dev, timed, rank, views=16, steps=4):
                 info={'workload': f'stage1_cars_recons16v (reference config): {scenes} scenes x {views} views {IMG}x{IMG} per GPU, {inner} optimiser '
                                   f'steps per train_step ({train_cfg["extra_scene_step"]} code-only + 1 joint with decoder-weight gradients), '
                                   f'{train_cfg["n_decoder_rays"]} rays/scene/step', 'last_log_vars': log})
+
+
+def train_stage2_measurement(dev, timed, rank, steps=4):
+    """`stage2_cars_uncond` (reference config, resolved): the denoiser (122 M parameters) trained on stored scene latents, samples_per_gpu
+    scenes per rank: diffusion loss forward + UNet input / weight-gradient pass + Adam step; at N > 1 the gradient all-reduce (NCCL) is
+    inside the step."""
+    import ssdnerf_b200 as S
+    cfg = reference_config('configs/paper_cfgs/stage2_cars_uncond.py')
+    torch.manual_seed(0)
+    model = S.build_model(cfg['model'], train_cfg=cfg['train_cfg'], test_cfg=cfg['test_cfg'])
+    g = torch.Generator().manual_seed(0)
+    for p in model.diffusion.denoising.parameters():
+        if p.dim() > 1:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    model = model.to(dev).train()
+    scenes = cfg['samples_per_gpu']
+    g = torch.Generator().manual_seed(200 + rank)
+    stored = [dict(param=dict(code=torch.tanh(torch.randn(3, 6, 128, 128, generator=g)) * 0.8, density_grid=torch.zeros(64 ** 3).half(),
+                              density_bitfield=torch.zeros(64 ** 3 // 8, dtype=torch.uint8))) for _ in range(scenes)]
+    data = dict(scene_id=list(range(scenes)), scene_name=[f's{i}' for i in range(scenes)], code=stored)
+    opt = dict(diffusion=torch.optim.Adam(model.diffusion.parameters(), lr=1e-4))
+    log = {}
+
+    def step():
+        log.update(model.train_step(data, opt)['log_vars'])
+    ms = timed(step, steps, 3)
+    if not all(v == v for v in log.values()):
+        raise RuntimeError(f'stage-2 training step produced non-finite values: {log}')
+    return dict(ms=ms, scenes=scenes,
+                info={'workload': f'stage2_cars_uncond (reference config): {scenes} stored scenes per GPU, diffusion loss + UNet forward / input-gradient / '
+                                  f'weight-gradient pass + Adam on 122 M parameters', 'last_log_vars': {k: v for k, v in log.items() if 'quartile' not in k}})
 
 
 def guided_measurement(dev, ev, stream, scenes=8, evals=6):
