@@ -161,7 +161,7 @@ class TriPlaneDecoder(VolumeRenderer):
         train-branch renderer (csrc/render_train.cu)."""
         if torch.is_grad_enabled() and (code.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             raise NotImplementedError('TriPlaneDecoder.point_decode is forward-only; gradients w.r.t. the code flow through the fused '
-                                      'differentiable renderer (decoder.forward in train mode), decoder-weight gradients are SURVEY.md §8 f2')
+                                      'differentiable renderer (decoder.forward in train mode), which also produces the decoder-weight gradients')
         if self.code_dropout is not None and self.training:
             raise NotImplementedError('code_dropout > 0 is unused by every reference config and not built')
         N.require_cuda(code)

@@ -200,8 +200,9 @@ class DenoisingUnetMod(nn.Module):
 
     def forward(self, x_t, t, label=None, concat_cond=None, return_noise=False):
         """denoising.py:191-216. x_t [B,C,H,W] float; t [B] long. Returns fp32 [B,C,H,W].
-        Differentiable w.r.t. x_t (weights are treated as frozen constants): when autograd is recording and x_t requires a gradient
-        the forward keeps its activations and `backward` runs the hand-written input-gradient pass (`UNetEngine.backward_nhwc`)."""
+        Differentiable: when autograd is recording the forward keeps its activations (save mode) and `backward` walks them with the
+        hand-written passes -- frozen parameters + x_t requiring a gradient: input-gradient pass only (`UNetEngine.backward_nhwc`);
+        any parameter requiring a gradient (training): input- and weight-gradient pass in one walk (`unet_train._UNetFullGrad`)."""
         if label is not None:
             raise NotImplementedError('class-conditional embedding is not built (num_classes == 0 in every reference config)')
         N.require_cuda(x_t)
@@ -227,7 +228,8 @@ class DenoisingUnetMod(nn.Module):
 
 
 class _UNetInputGrad(torch.autograd.Function):
-    """v = UNet(x_t, t) with d v / d x_t by the native input-gradient pass (weights frozen: guidance / val_optim never train them)."""
+    """v = UNet(x_t, t) with d v / d x_t by the native input-gradient pass (frozen weights: guidance / val_optim never train them;
+    training goes through unet_train._UNetFullGrad)."""
 
     @staticmethod
     def forward(ctx, x_t, module, t):
@@ -527,7 +529,7 @@ class UNetEngine:
         self.saving = False
         return self.v_out
 
-    # ------------------------------------------------------------------ input-gradient pass (weights frozen)
+    # ------------------------------------------------------------------ input-gradient pass (+ weight-gradient hooks: unet_train.py)
     def _pack_backward_weights(self):
         """transposed / tap-flipped fp16 copies of every weight, packed on first use (guidance and val_optim only)"""
         m, dev = self.m, self.dev

@@ -157,10 +157,12 @@ def test_full_size_unet_weight_gradients(cuda):
 
 
 def test_dropout_training_forward_backward_consistent(cuda):
-    """dropout 0.1 (the recons configs): the backward and the weight-gradient pass regenerate the forward's mask -- finite-difference
-    check of d(v . r) along a random weight direction with the seed held fixed"""
+    """ResBlock dropout (0.1 in the recons configs; 0.5 here so that a wrong mask would halve the correlation): the backward and the
+    weight-gradient pass regenerate the forward's mask -- finite-difference check of d(v . r) along a random direction of the weight
+    right behind the dropout, seed held fixed.  The bar (30 %) covers the fp16 run-to-run noise of two forwards (~10 % of the
+    difference at this step size) plus the third-order term of the central difference; a mask mismatch shows up as ~50 %."""
     from ssdnerf_b200.unet import DenoisingUnetMod
-    cfg = dict(SMALL, dropout=0.1)
+    cfg = dict(SMALL, dropout=0.5)
     m = DenoisingUnetMod(**cfg)
     g = torch.Generator().manual_seed(5)
     with torch.no_grad():
@@ -184,7 +186,7 @@ def test_dropout_training_forward_backward_consistent(cuda):
         assert _rel_l2(m(x, t), v.detach()) > 2e-2               # eval: no dropout
     m.train()
     p = dict(m.named_parameters())['mid_blocks.0.conv_2.2.weight']          # the convolution right behind the dropout
-    d = torch.randn_like(p) * 0.02
+    d = torch.randn_like(p) * 0.01
     ana = float((p.grad * d).sum())
     vals = []
     for sgn in (1, -1):
@@ -196,4 +198,4 @@ def test_dropout_training_forward_backward_consistent(cuda):
             p.sub_(sgn * d)
     num = (vals[0] - vals[1]) / 2
     print('dropout directional derivative: analytic', ana, 'finite difference', num)
-    assert abs(ana - num) < 0.08 * abs(num) + 1e-3
+    assert abs(ana - num) < 0.3 * abs(num) + 1e-3
