@@ -43,9 +43,10 @@ class WeightGradPass:
         return self.eng._buf(('wg', 'csum', C), (self.eng.B, C, 2), torch.float32)
 
     def _add(self, param, g):
+        """g: a tensor this pass owns (fresh buffer or a view of one) -- stored as is, no defensive copy"""
         g = g.reshape(param.shape)
         old = self.grads.get(param)
-        self.grads[param] = g.clone() if old is None else old.add_(g)
+        self.grads[param] = g if old is None else old.add_(g)
 
     def _conv(self, weight, bias, gy, xs, taps=1, stride=1, up=False):
         """gy fp16 [B,Ho,Wo,Cg>=cout]; xs = list of (tensor [B,Hi,Wi,Cx], channels used) concatenated along the input-channel axis"""
@@ -168,8 +169,7 @@ class WeightGradPass:
     # ------------------------------------------------------------------ wrap-up
     def finish(self, inv_scale):
         """un-scale (inv_scale: 0-dim device tensor = 1 / loss scale); returns (grads dict, d loss / d scale-shift rows [B, ss_total])"""
-        for g in self.grads.values():
-            g.mul_(inv_scale)
+        torch._foreach_mul_(list(self.grads.values()), inv_scale)
         return self.grads, self.d_ss * inv_scale
 
 
