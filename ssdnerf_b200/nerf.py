@@ -25,7 +25,7 @@ from . import _lib as N
 from . import density as D
 from . import renderer as R
 from .registry import MODELS, MODULES, build_module
-from .scene_cache import SceneCache
+from .scene_cache import SceneCache, restore_optimizer_state
 
 
 # --------------------------------------------------------------------------------------------------------------------- small modules
@@ -629,7 +629,7 @@ class MultiSceneNeRF(BaseNeRF):
         code_optimizers = self.build_optimizer(code_list_, self.train_cfg)
         for opt, st in zip(code_optimizers, states):
             if st is not None and st.get('optimizer') is not None:
-                opt.load_state_dict(st['optimizer'])          # casts the stored moments to the latent's device / dtype
+                restore_optimizer_state(opt, st['optimizer'])
         return code_list_, code_optimizers, torch.stack(grids), torch.stack(bitfields)
 
     def save_cache(self, code_list_, code_optimizers, density_grid, density_bitfield, scene_id, scene_name):

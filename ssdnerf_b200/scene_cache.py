@@ -58,6 +58,30 @@ def optimizer_state_record(state_dict, dtype, into=None):
     return out
 
 
+def restore_optimizer_state(optimizer, record):
+    """Put a cached per-parameter state (moments, step) back into a freshly built optimizer.  Unlike `Optimizer.load_state_dict` the
+    hyper-parameters of the record's `param_groups` are NOT restored: the optimizer keeps the learning rate etc. of the CURRENT
+    train_cfg, which is what the reference's `optimizer_set_state` (lib/core/utils/misc.py:85-126) does.  Float state is cast to the
+    parameter's dtype and device; `step` keeps its own."""
+    saved = [pid for g in record['param_groups'] for pid in g['params']]
+    live = [p for g in optimizer.param_groups for p in g['params']]
+    if len(saved) != len(live):
+        raise ValueError('cached optimizer state does not match the optimizer (different number of parameters)')
+    for pid, param in zip(saved, live):
+        st = record['state'].get(pid)
+        if st is None:
+            continue
+        new = {}
+        for k, v in st.items():
+            if isinstance(v, torch.Tensor):
+                if k == 'step':          # Adam keeps its step counter on the host unless capturable / fused: leave it where it is
+                    v = v.clone()
+                else:
+                    v = v.to(device=param.device, dtype=param.dtype if v.is_floating_point() else None, copy=True)
+            new[k] = v
+        optimizer.state[param] = new
+
+
 def shard_bounds(cache_size, world_size):
     """scene-index split points of the reference (multiscene_nerf.py:49): np.round(np.linspace(0, cache_size, ws + 1))"""
     return np.round(np.linspace(0, cache_size, num=world_size + 1)).astype(np.int64)

@@ -90,3 +90,61 @@ def test_stored_activated_code_is_inverted():
     codes, opts, _, _ = m.load_cache(dict(scene_id=[7], scene_name=['x'], code=[rec]))
     np.testing.assert_allclose(m.code_activation(codes[0]).detach().numpy(), code.numpy(), atol=1e-5)
     assert m.cache is None
+
+
+def test_cache_matches_reference_execution():
+    """replay of tests/golden/make_golden_cache.py's visit sequence: every tensor the REFERENCE's own load_cache / save_cache left in its
+    cache or handed back (fixture produced by executing multiscene_nerf.py + misc.py) vs `ssdnerf_b200.MultiSceneNeRF`"""
+    import ssdnerf_b200 as S
+    ref = np.load(os.path.join(GOLDEN, 'reference_cache_v1.npz'))
+    CODE_SIZE, GRID = (3, 2, 4, 4), 8
+    m = S.build_model(dict(type='MultiSceneNeRF', code_size=CODE_SIZE, grid_size=GRID, cache_size=2, cache_16bit=True,
+                           decoder=dict(type='TriPlaneDecoder')), train_cfg=dict(optimizer=dict(type='Adam', lr=0.01, weight_decay=0.0)))
+    scene_id, names = [1, 0], ['b', 'a']
+    fresh = iter(())
+    m.get_init_code_ = lambda n, device=None: next(fresh)
+
+    def check(tag):
+        for sid in (0, 1):
+            e = m.cache[sid]
+            assert str(e['param']['code_'].dtype) == str(ref[f'{tag}_s{sid}_code_dtype']) == 'torch.float16'
+            assert str(e['param']['density_grid'].dtype) == str(ref[f'{tag}_s{sid}_grid_dtype'])
+            assert np.array_equal(e['param']['code_'].float().numpy(), ref[f'{tag}_s{sid}_code'])          # incl. the saturated +-65504
+            assert np.array_equal(e['param']['density_grid'].float().numpy(), ref[f'{tag}_s{sid}_grid'])
+            assert np.array_equal(e['param']['density_bitfield'].numpy(), ref[f'{tag}_s{sid}_bits'])
+            st = e['optimizer']['state'][0]
+            assert float(st['step']) == float(ref[f'{tag}_s{sid}_step'])
+            assert str(st['exp_avg'].dtype) == str(ref[f'{tag}_s{sid}_moment_dtype']) == 'torch.bfloat16'
+            assert np.array_equal(st['exp_avg'].float().numpy(), ref[f'{tag}_s{sid}_exp_avg'])
+            assert np.array_equal(st['exp_avg_sq'].float().numpy(), ref[f'{tag}_s{sid}_exp_avg_sq'])
+            assert sorted(e.keys()) == list(ref[f'{tag}_s{sid}_keys']) and e['scene_name'] == str(ref[f'{tag}_s{sid}_name'])
+
+    def visit(tag, n_steps, k0, save=True):
+        nonlocal fresh
+        fresh = iter([torch.from_numpy(ref[f'init_{s}']).clone().requires_grad_(True) for s in scene_id])
+        codes, opts, grid, bits = m.load_cache(dict(scene_id=scene_id, scene_name=names))
+        for i, s in enumerate(scene_id):
+            assert np.array_equal(codes[i].detach().numpy(), ref[f'{tag}_loaded_s{s}_code']), (tag, s)
+            assert codes[i].requires_grad and codes[i].dtype == torch.float32
+            assert opts[i].param_groups[0]['lr'] == float(ref[f'{tag}_loaded_s{s}_lr'])      # the CURRENT config's lr, not the cached one
+            sd = opts[i].state_dict()['state']
+            assert (len(sd) > 0) == bool(ref[f'{tag}_loaded_s{s}_has_state'])
+            if len(sd) > 0:
+                assert str(sd[0]['exp_avg'].dtype) == str(ref[f'{tag}_loaded_s{s}_state_dtype']) == 'torch.float32'
+                assert np.array_equal(sd[0]['exp_avg'].numpy(), ref[f'{tag}_loaded_s{s}_exp_avg'])
+                assert float(sd[0]['step']) == float(ref[f'{tag}_loaded_s{s}_step'])
+        assert np.array_equal(grid.float().numpy(), ref[f'{tag}_loaded_grid']) and np.array_equal(bits.numpy(), ref[f'{tag}_loaded_bits'])
+        for k in range(n_steps):
+            for i, s in enumerate(scene_id):
+                codes[i].grad = torch.from_numpy(ref[f'grad_{s}_{k0 + k}']).clone()
+                opts[i].step()
+        if save:
+            grid = torch.stack([torch.from_numpy(ref[f'grid_{s}']).half() for s in scene_id]) * (1 if tag == 'v1' else 2)
+            bits = torch.stack([torch.from_numpy(ref[f'bits_{s}']) for s in scene_id])
+            m.save_cache(codes, opts, grid, bits, scene_id, names)
+            check(tag)
+
+    visit('v1', 2, 0)
+    m.train_cfg = dict(optimizer=dict(type='Adam', lr=0.02, weight_decay=0.0))
+    visit('v2', 1, 2)
+    visit('v3', 0, 0, save=False)
