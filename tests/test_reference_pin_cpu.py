@@ -227,3 +227,43 @@ def test_host_helpers_match_reference_executed(ref):
     assert np.array_equal(o.numpy(), ref['rs_o']) and np.array_equal(d.numpy(), ref['rs_d']) and np.array_equal(t.numpy(), ref['rs_t'])
     o, d, t = BaseNeRF.ray_sample(rays_o, rays_d, imgs, 20, sample_inds=inds[1])
     assert np.array_equal(o.numpy(), ref['rs_o_given']) and np.array_equal(t.numpy(), ref['rs_t_given'])
+
+
+def test_stage2_train_step_matches_reference_execution(ref):
+    """`DiffusionNeRF.train_step` (stage 2: stored scenes, denoiser optimizer only) for two consecutive iterations vs the fixture produced
+    by executing the reference's own train_step / forward_train / DDPMMSELossMod (training mode) / load_scene
+    (tests/golden/make_golden_train_step.py): loss, log_vars, running norm factor and the SGD-updated denoiser weights.  The oracle UNet stands
+    in for the CUDA engine (same seeded weights as the reference UNet of the fixture); timestep draw and noise are injected on both sides."""
+    import ssdnerf_b200 as S
+    tr = np.load(os.path.join(GOLDEN, 'reference_train_step_v1.npz'))
+    m = S.build_model(dict(
+        type='DiffusionNeRF', code_size=(3, 6, 16, 16), code_reshape=(18, 16, 16), grid_size=8, diffusion_use_ema=False, decoder_use_ema=True,
+        freeze_decoder=True, decoder=dict(type='TriPlaneDecoder', base_layers=[18, 64], density_layers=[64, 1], color_layers=[64, 3],
+                                          use_dir_enc=True, dir_layers=[16, 64]),
+        diffusion=dict(type='GaussianDiffusion', num_timesteps=1000, betas_cfg=dict(type='linear'), denoising_mean_mode='V',
+                       denoising=dict(type='DenoisingUnetMod', image_size=16, in_channels=18, base_channels=64, channels_cfg=[1],
+                                      resblocks_per_downsample=1, use_scale_shift_norm=True, attention_res=[]),
+                       timestep_sampler=dict(type='SNRWeightedTimeStepSampler', power=0.5),
+                       ddpm_loss=dict(type='DDPMMSELossMod', rescale_mode='timestep_weight', data_info=dict(pred='v_t_pred', target='v_t'),
+                                      weight_scale=4.0, scale_norm=True, loss_name='loss_ddpm_mse'))), train_cfg=dict(), test_cfg=dict())
+    unet = _OracleUNet(ref)
+    m.diffusion.denoising = unet
+    m.train()
+    assert all(p.requires_grad for p in unet.parameters()) and not any(p.requires_grad for p in m.decoder.parameters())
+    opt = dict(diffusion=torch.optim.SGD(m.diffusion.parameters(), lr=float(tr['lr'])))
+    data = dict(scene_id=[0, 1], scene_name=['a', 'b'], code=[dict(param=dict(code=torch.from_numpy(c))) for c in tr['codes']])
+    plain = m.diffusion.forward_train
+    for it in range(2):
+        t, noise = torch.from_numpy(tr['t'][it]), torch.from_numpy(tr['noise'][it])
+        m.diffusion.forward_train = lambda x0, t=t, noise=noise, **kw: plain(x0, t=t, noise=noise, **kw)
+        res = m.train_step(data, opt)
+        lv = res['log_vars']
+        assert sorted(lv.keys()) == list(tr[f'it{it}_log_keys']) and res['num_samples'] == int(tr[f'it{it}_num_samples'])
+        assert abs(lv['loss_ddpm_mse'] - float(tr[f'it{it}_loss'])) <= 2e-5 * abs(float(tr[f'it{it}_loss'])), (it, lv)
+        _close(m.diffusion.ddpm_loss.norm_factor, tr[f'it{it}_norm_factor'], 1e-7)
+        sd = {k.replace('/', '.'): v.detach() for k, v in unet.sd.items()}
+        for k in tr['probe_names']:
+            ref_w = tr[f'it{it}_{k}']
+            _close(sd[str(k)], ref_w, 2e-6 + 2e-5 * float(np.abs(ref_w).max()))
+        chk = sum(float(v.double().abs().sum()) for v in sd.values())
+        assert abs(chk - float(tr[f'it{it}_param_checksum'])) <= 1e-6 * float(tr[f'it{it}_param_checksum'])
