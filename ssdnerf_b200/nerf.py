@@ -534,7 +534,7 @@ class BaseNeRF(nn.Module):
         if data.get('test_imgs') is not None:
             target = data['test_imgs'].permute(0, 1, 4, 2, 3).reshape(num_scenes * num_imgs, 3, h, w)
             mse = (pred_imgs - target).square().flatten(1).mean(dim=1)
-            log_vars.update(test_psnr=float((-10 * torch.log10(mse.clamp_min(1e-12))).mean()))
+            log_vars.update(test_psnr=float((-10 * torch.log10(mse + 1e-6)).mean()))          # eval_psnr (lib/core/evaluation/metrics.py:52-55): eps 1e-6
         return log_vars, pred_imgs.reshape(num_scenes, num_imgs, 3, h, w)
 
     def mean_ema_update(self, code):
@@ -644,7 +644,6 @@ class MultiSceneNeRF(BaseNeRF):
     def train_step(self, data, optimizer, running_status=None):
         """multiscene_nerf.py:185-252: optional extra code-only steps, then ONE joint step of the scene latents (their own
         optimizers) and the decoder (`optimizer['decoder']`) on `n_decoder_rays` random rays per scene."""
-        N.require_cuda(data['cond_imgs'], data['cond_poses'], data['cond_intrinsics'])
         code_list_, code_optimizers, density_grid, density_bitfield = self.load_cache(data)
         cond_imgs, cond_intrinsics, cond_poses = data['cond_imgs'], data['cond_intrinsics'], data['cond_poses']
         num_scenes, num_imgs, h, w, _ = cond_imgs.size()
@@ -677,7 +676,7 @@ class MultiSceneNeRF(BaseNeRF):
         with torch.no_grad():
             self.mean_ema_update(code)
             mse = (out_rgbs.reshape(num_scenes, -1) - target_rgbs.reshape(num_scenes, -1)).square().mean(dim=1)
-            log_vars.update(train_psnr=float((-10 * torch.log10(mse.clamp_min(1e-12))).mean()),
+            log_vars.update(train_psnr=float((-10 * torch.log10(mse + 1e-6)).mean()),
                             code_rms=float(code.square().flatten(1).mean().sqrt()))
             if data.get('test_imgs', None) is not None:
                 log_vars.update(self.eval_and_viz(data, self.decoder, code, density_bitfield, cfg=self.train_cfg)[0])
@@ -811,7 +810,7 @@ class DiffusionNeRF(MultiSceneNeRF):
                 if len(code_optimizers) > 0:
                     self.mean_ema_update(code)
                 mse = (out_rgbs.reshape(num_scenes, -1) - target_rgbs.reshape(num_scenes, -1)).square().mean(dim=1)
-                log_vars.update(train_psnr=float((-10 * torch.log10(mse.clamp_min(1e-12))).mean()),
+                log_vars.update(train_psnr=float((-10 * torch.log10(mse + 1e-6)).mean()),
                                 code_rms=float(code.square().flatten(1).mean().sqrt()))
                 if data.get('test_imgs', None) is not None:
                     log_vars.update(self.eval_and_viz(data, self.decoder, code, density_bitfield, cfg=self.train_cfg)[0])

@@ -70,3 +70,34 @@ def seeded_weights(keys, shapes, seed):
 
 def parse_shapes(arr):
     return [tuple(int(x) for x in s.split(',')) if s else () for s in arr.tolist()]
+
+
+class ToyDecoder(torch.nn.Module):
+    """Pure-torch stand-in for the volume renderer behind the decoder interface (`forward(rays_o, rays_d, code, density_bitfield, grid_size,
+    dt_gamma=, perturb=, return_loss=) -> dict(weights_sum, depth, image[, decoder_reg_loss])`).  Test infrastructure for HOST-LOGIC pins only:
+    tests/golden/make_golden_joint_step.py runs the reference's own `train_step`s with it on CPU and tests/test_reference_pin_cpu.py replays
+    the same sequence through ssdnerf_b200's.  It is differentiable w.r.t. the code and its own weights; rays select code texels."""
+
+    def __init__(self, channels=18, seed=3):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.lin = torch.nn.Linear(channels, 3)
+        self.head = torch.nn.Linear(channels, 1)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+        self.bound, self.min_near, self.max_steps = 1, 0.2, 8
+
+    def forward(self, rays_o, rays_d, code, density_bitfield, grid_size, dt_gamma=0, perturb=False, T_thresh=1e-4, return_loss=False):
+        B = code.size(0)
+        feat = code.reshape(B, code.size(1) * code.size(2), -1)                         # [B, 18, h*w]
+        idx = ((rays_d[..., 0] * 7.3 + rays_d[..., 2] * 1.9 + rays_o[..., 1] * 3.1).abs() * 1000).long() % feat.size(-1)   # [B, N]
+        f = feat.gather(2, idx[:, None, :].expand(-1, feat.size(1), -1)).transpose(1, 2)                                     # [B, N, 18]
+        ws = torch.sigmoid(self.head(f)).squeeze(-1)
+        out = dict(weights_sum=ws, depth=ws.detach() * 2.0, image=torch.sigmoid(self.lin(f)) * ws.unsqueeze(-1))
+        if return_loss:
+            out.update(decoder_reg_loss=None)
+        return out
+
+    def _fused_train_ok(self, *args):        # ssdnerf_b200.BaseNeRF.loss asks the decoder whether the fused native route applies
+        return False

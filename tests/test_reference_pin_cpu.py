@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import unet_port as up
+from oracle.render_port import get_cam_rays as rp_get_cam_rays
 from tests.common import GOLDEN, parse_shapes, seeded_weights
 
 
@@ -267,3 +268,83 @@ def test_stage2_train_step_matches_reference_execution(ref):
             _close(sd[str(k)], ref_w, 2e-6 + 2e-5 * float(np.abs(ref_w).max()))
         chk = sum(float(v.double().abs().sum()) for v in sd.values())
         assert abs(chk - float(tr[f'it{it}_param_checksum'])) <= 1e-6 * float(tr[f'it{it}_param_checksum'])
+
+
+def _replay_checks(jt, tag, model, res, decoder, atol=2e-6):
+    lv = res['log_vars']
+    assert sorted(lv.keys()) == list(jt[f'{tag}_log_keys']), (sorted(lv.keys()), list(jt[f'{tag}_log_keys']))
+    got = np.array([lv[k] for k in sorted(lv.keys())], np.float64)
+    np.testing.assert_allclose(got, jt[f'{tag}_log_vals'], rtol=5e-5, atol=1e-7, err_msg=f'{tag} log_vars {sorted(lv.keys())}')
+    assert res['num_samples'] == int(jt[f'{tag}_num_samples'])
+    for k, v in decoder.state_dict().items():
+        _close(v, jt[f'{tag}_dec_{k}'], atol)
+    _close(model.init_code, jt[f'{tag}_init_code'], atol)
+    for sid, e in model.cache.items():
+        assert (e is not None) == bool(jt[f'{tag}_cache{sid}_filled']), (tag, sid)
+        if e is not None:
+            assert e['param']['code_'].dtype == torch.float16
+            _close(e['param']['code_'].float(), jt[f'{tag}_cache{sid}_code'], 1e-3)          # fp16 storage: one ulp at |x| <= 2 is 9.8e-4
+            assert float(e['optimizer']['state'][0]['step']) == float(jt[f'{tag}_cache{sid}_step'])
+            _close(e['optimizer']['state'][0]['exp_avg'].float(), jt[f'{tag}_cache{sid}_exp_avg'], 2e-3)
+
+
+def test_joint_train_steps_match_reference_execution(ref, monkeypatch):
+    """`MultiSceneNeRF.train_step` (stage 1) and `DiffusionNeRF.train_step` (single stage), two iterations each over overlapping scene sets,
+    vs the fixture produced by executing the reference's own train_steps through their real constructors
+    (tests/golden/make_golden_joint_step.py).  Both sides use tests/common.py:ToyDecoder as the renderer and skip the occupancy update (the
+    reference's needs its CUDA extension); log_vars, decoder weights after Adam, the running mean code, every cache entry (latent, Adam
+    step count and first moment) and, for the single-stage step, the SGD-updated denoiser and its loss normaliser are compared."""
+    import ssdnerf_b200 as S
+    from ssdnerf_b200 import nerf as nerf_mod
+    from tests.common import ToyDecoder
+    jt = np.load(os.path.join(GOLDEN, 'reference_joint_step_v1.npz'))
+    tr = np.load(os.path.join(GOLDEN, 'reference_train_step_v1.npz'))
+    if 'ToyDecoder' not in S.MODULES._module_dict:
+        S.MODULES.register_module(name='ToyDecoder', module=ToyDecoder)
+    monkeypatch.setattr(nerf_mod.R, 'get_cam_rays', lambda c2w, intr, h, w: rp_get_cam_rays(c2w, intr, h, w))
+    train1 = dict(optimizer=dict(type='Adam', lr=0.01, weight_decay=0.0), n_decoder_rays=40, n_inverse_rays=48, extra_scene_step=3,
+                  loss_coef=0.01, dt_gamma_scale=0.5, density_thresh=0.1)
+    model1 = dict(code_size=(3, 6, 8, 8), grid_size=8, code_activation=dict(type='TanhCode', scale=2), bg_color=1, init_from_mean=True,
+                  pixel_loss=dict(type='MSELoss', loss_weight=20.0), reg_loss=dict(type='TVLoss', power=1.5, loss_weight=1.0),
+                  decoder=dict(type='ToyDecoder'), decoder_use_ema=False, cache_size=3, cache_16bit=True)
+    imgs, poses, intr = (torch.from_numpy(jt[k]) for k in ('s1_imgs', 's1_poses', 's1_intr'))
+
+    def batch(ids):
+        return dict(scene_id=ids, scene_name=[f's{i}' for i in ids], cond_imgs=imgs[ids], cond_poses=poses[ids], cond_intrinsics=intr[ids])
+    # ---- stage 1
+    m1 = S.build_model(dict(type='MultiSceneNeRF', **model1), train_cfg=dict(train1), test_cfg=dict())
+    m1.update_extra_state = lambda *a, **k: None
+    m1.train()
+    opt = dict(decoder=torch.optim.Adam(m1.decoder.parameters(), lr=1e-3))
+    torch.manual_seed(123)
+    for it, ids in enumerate(([2, 0], [0, 1])):
+        _replay_checks(jt, f's1_it{it}', m1, m1.train_step(batch(ids), opt), m1.decoder)
+    # ---- single stage
+    m2 = S.build_model(dict(
+        type='DiffusionNeRF', **dict(model1, code_size=(3, 6, 16, 16)), code_reshape=(18, 16, 16), freeze_decoder=False, diffusion_use_ema=False,
+        diffusion=dict(type='GaussianDiffusion', num_timesteps=1000, betas_cfg=dict(type='linear'), denoising_mean_mode='V',
+                       denoising=dict(type='DenoisingUnetMod', image_size=16, in_channels=18, base_channels=64, channels_cfg=[1],
+                                      resblocks_per_downsample=1, use_scale_shift_norm=True, attention_res=[]),
+                       timestep_sampler=dict(type='SNRWeightedTimeStepSampler', power=0.5),
+                       ddpm_loss=dict(type='DDPMMSELossMod', rescale_mode='timestep_weight', data_info=dict(pred='v_t_pred', target='v_t'),
+                                      weight_scale=4.0, scale_norm=True, loss_name='loss_ddpm_mse'))),
+        train_cfg=dict(train1, optimizer=dict(type='Adam', lr=0.005, weight_decay=0.0), extra_scene_step=2), test_cfg=dict())
+    unet = _OracleUNet(ref)
+    m2.diffusion.denoising = unet
+    m2.update_extra_state = lambda *a, **k: None
+    m2.train()
+    opt = dict(diffusion=torch.optim.SGD(m2.diffusion.parameters(), lr=0.05), decoder=torch.optim.Adam(m2.decoder.parameters(), lr=1e-3))
+    plain = m2.diffusion.forward_train
+    torch.manual_seed(321)
+    for it, ids in enumerate(([2, 0], [0, 1])):
+        t, noise = torch.from_numpy(jt['s2_t'][it]), torch.from_numpy(jt['s2_noise'][it])
+        m2.diffusion.forward_train = lambda x0, t=t, noise=noise, **kw: plain(x0, t=t, noise=noise, **kw)
+        tag = f's2_it{it}'
+        _replay_checks(jt, tag, m2, m2.train_step(batch(ids), opt), m2.decoder)
+        _close(m2.diffusion.ddpm_loss.norm_factor, jt[f'{tag}_norm_factor'], 1e-7)
+        sd = {k.replace('/', '.'): v.detach() for k, v in unet.sd.items()}
+        for k in tr['probe_names']:
+            w = jt[f'{tag}_unet_{k}']
+            _close(sd[str(k)], w, 2e-6 + 2e-5 * float(np.abs(w).max()))
+        chk = sum(float(v.double().abs().sum()) for v in sd.values())
+        assert abs(chk - float(jt[f'{tag}_unet_checksum'])) <= 1e-6 * float(jt[f'{tag}_unet_checksum'])
