@@ -867,9 +867,8 @@ class DiffusionNeRF(MultiSceneNeRF):
 
     def _cond_rays(self, data):
         cond_imgs, cond_intrinsics, cond_poses = data['cond_imgs'], data['cond_intrinsics'], data['cond_poses']
-        N.require_cuda(cond_imgs, cond_intrinsics, cond_poses)
         num_scenes, num_imgs, h, w, _ = cond_imgs.size()
-        cond_rays_o, cond_rays_d = R.get_cam_rays(cond_poses, cond_intrinsics, h, w)
+        cond_rays_o, cond_rays_d = R.get_cam_rays(cond_poses, cond_intrinsics, h, w)          # native: refuses CPU tensors
         dt_gamma = self.test_cfg.get('dt_gamma_scale', 0.0) / cond_intrinsics[..., :2].mean(dim=(-2, -1))
         if self.image_cond:
             raise NotImplementedError('image-conditioned (concat_cond) denoisers are not used by the shipped configs')

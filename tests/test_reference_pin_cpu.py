@@ -348,3 +348,66 @@ def test_joint_train_steps_match_reference_execution(ref, monkeypatch):
             _close(sd[str(k)], w, 2e-6 + 2e-5 * float(np.abs(w).max()))
         chk = sum(float(v.double().abs().sum()) for v in sd.values())
         assert abs(chk - float(jt[f'{tag}_unet_checksum'])) <= 1e-6 * float(jt[f'{tag}_unet_checksum'])
+
+
+def test_val_paths_match_reference_execution(ref, monkeypatch):
+    """BASELINE config 4's host logic: `val_guide` (render-loss guidance through the denoiser + langevin), `val_optim` (diffusion-prior
+    gradient, inner render-loss Adam steps from that gradient, ExponentialLR) and `val_uncond` (intermediates list + prior-only refinement)
+    vs the fixture produced by executing the reference's own methods through the real `DiffusionNeRF` constructor
+    (tests/golden/make_golden_val.py; toy renderer and no-op occupancy calls on both sides, draws injected)."""
+    import ssdnerf_b200 as S
+    from ssdnerf_b200 import nerf as nerf_mod
+    from tests.common import ToyDecoder
+    vf = np.load(os.path.join(GOLDEN, 'reference_val_v1.npz'))
+    if 'ToyDecoder' not in S.MODULES._module_dict:
+        S.MODULES.register_module(name='ToyDecoder', module=ToyDecoder)
+    monkeypatch.setattr(nerf_mod.R, 'get_cam_rays', lambda c2w, intr, h, w: rp_get_cam_rays(c2w, intr, h, w))
+    test_cfg = dict(num_timesteps=4, clip_range=[-2, 2], guidance_gain=50.0, snr_weight_power=0.25, langevin_steps=1, langevin_delta=0.4,
+                    n_inverse_rays=48, n_inverse_steps=3, extra_scene_step=2, optimizer=dict(type='Adam', lr=0.005, weight_decay=0.0),
+                    lr_scheduler=dict(type='ExponentialLR', gamma=0.9), loss_coef=0.01, dt_gamma_scale=0.5, density_thresh=0.1)
+    m = S.build_model(dict(
+        type='DiffusionNeRF', code_size=(3, 6, 16, 16), grid_size=8, code_activation=dict(type='TanhCode', scale=2), bg_color=1,
+        pixel_loss=dict(type='MSELoss', loss_weight=20.0), reg_loss=dict(type='TVLoss', power=1.5, loss_weight=1.0),
+        decoder=dict(type='ToyDecoder'), decoder_use_ema=False, code_reshape=(18, 16, 16), freeze_decoder=True, diffusion_use_ema=False,
+        diffusion=dict(type='GaussianDiffusion', num_timesteps=1000, betas_cfg=dict(type='linear'), denoising_mean_mode='V',
+                       denoising=dict(type='DenoisingUnetMod', image_size=16, in_channels=18, base_channels=64, channels_cfg=[1],
+                                      resblocks_per_downsample=1, use_scale_shift_norm=True, attention_res=[]),
+                       timestep_sampler=dict(type='SNRWeightedTimeStepSampler', power=0.25),
+                       ddpm_loss=dict(type='DDPMMSELossMod', rescale_mode='timestep_weight', data_info=dict(pred='v_t_pred', target='v_t'),
+                                      weight_scale=4.0, scale_norm=True, loss_name='loss_ddpm_mse'))), train_cfg=dict(), test_cfg=dict(test_cfg))
+    m.diffusion.denoising = _OracleUNet(ref)
+    m.update_extra_state = lambda *a, **k: None
+    m.get_density = lambda decoder, code, cfg=dict(): (torch.zeros(code.size(0), 8 ** 3), torch.zeros(code.size(0), 8 ** 3 // 8, dtype=torch.uint8))
+    m.eval()
+    m.diffusion.ddpm_loss.norm_factor.fill_(0.6)
+    t = lambda k: torch.from_numpy(vf[k])
+    lang, ts, eps = list(t('lang')), list(t('ts')), list(t('eps'))
+    data = dict(scene_id=[0, 1], scene_name=['a', 'b'], cond_imgs=t('imgs'), cond_poses=t('poses'), cond_intrinsics=t('intr'), noise=t('noise'))
+    plain = m.diffusion.forward_train
+
+    def inject(t_list, n_list):
+        it_t, it_n = iter(t_list), iter(n_list)
+        m.diffusion.forward_train = lambda x0, **kw: plain(x0, t=next(it_t), noise=next(it_n), **kw)
+    # ---- guided sampling
+    torch.manual_seed(77)
+    with torch.no_grad():
+        code, _, _ = m.val_guide(data, langevin_noises=iter(lang[:3]))
+    err = float((code - t('guide_code')).abs().max())
+    print('val_guide max abs diff vs reference execution', err)
+    _close(code, vf['guide_code'], 2e-4)
+    # ---- code optimisation with the diffusion prior
+    inject(ts, eps)
+    torch.manual_seed(78)
+    with torch.no_grad():
+        code, _, _ = m.val_optim(data, code_=t('code0').clone().requires_grad_(True))
+    print('val_optim max abs diff', float((code - t('optim_code')).abs().max()))
+    _close(code, vf['optim_code'], 5e-5)
+    # ---- unconditional sampling with intermediates + prior-only refinement (the fixture's draw order: 3 langevin, then 3 loss noises)
+    assert int(vf['uncond_noise_calls']) == 6
+    inject(ts[3:], [lang[3], eps[3], eps[4]])
+    torch.manual_seed(79)
+    with torch.no_grad():
+        codes, grids, bits = m.val_uncond(dict(scene_id=[0, 1], noise=t('noise')), save_intermediates=True, langevin_noises=iter(lang[:3]))
+    assert len(codes) == int(vf['uncond_len']) == len(grids) == len(bits)
+    _close(codes[0], vf['uncond_first'], 5e-5)
+    _close(codes[-1], vf['uncond_last'], 2e-4)
