@@ -411,3 +411,70 @@ def test_val_paths_match_reference_execution(ref, monkeypatch):
     assert len(codes) == int(vf['uncond_len']) == len(grids) == len(bits)
     _close(codes[0], vf['uncond_first'], 5e-5)
     _close(codes[-1], vf['uncond_last'], 2e-4)
+
+
+def test_renderer_oracle_matches_reference_decoder_execution():
+    """The oracle restatements every GPU parity test of the fused renderers is measured against -- `render_port.point_decode`,
+    `render_port.render_eval_scene` (host loop of base_volume_renderer.py:79-123) and `train_port.render_train_scene` (train branch + K7 / K8
+    through autograd) -- vs the fixture produced by executing the reference's OWN `TriPlaneDecoder` and op wrappers over a `_backend` that
+    forwards to the kernel-exact C oracle (tests/golden/make_golden_decoder.py).  Also: our TriPlaneDecoder's state-dict layout."""
+    import ssdnerf_b200 as S
+    from oracle import render_port as rp
+    from oracle import train_port as tp
+    from tests.common import spiral_poses
+    D = np.load(os.path.join(GOLDEN, 'reference_decoder_v1.npz'))
+    res = 24
+    f = 131.25 * res / 128
+    poses = torch.from_numpy(spiral_poses(2)).float()
+    intr = torch.tensor([f, f, res / 2, res / 2]).expand(2, 4).contiguous()
+    ro, rd = rp.get_cam_rays(poses, intr, res, res)
+    ro, rd = ro.reshape(2, -1, 3).contiguous(), rd.reshape(2, -1, 3).contiguous()
+    bits = np.stack([rp.sphere_bitfield(radius=0.7), rp.sphere_bitfield(radius=0.5)])
+    dt_gamma = [0.0, 0.004]
+    cfgs = dict(P=dict(type='TriPlaneDecoder', base_layers=[18, 64], density_layers=[64, 1], color_layers=[64, 3], use_dir_enc=True,
+                       dir_layers=[16, 64], max_steps=256), S=dict(type='TriPlaneDecoder', max_steps=256))
+    for variant in ('P', 'S'):
+        C = 6 if variant == 'P' else 32
+        g = torch.Generator().manual_seed(int(D[f'{variant}_code_seed']))
+        code = (torch.randn(2, 3, C, 128, 128, generator=g) * 0.7).clamp(-2, 2)
+        params = rp.make_decoder_params(variant, 4)
+        params['density_net.0.bias'] = params['density_net.0.bias'] + 1.0
+        assert list(S.build_module(cfgs[variant]).state_dict().keys()) == list(D[f'{variant}_state_keys'])
+        # point_decode on the fixture's explicit points
+        xyz, dirs, counts = torch.from_numpy(D[f'{variant}_pd_xyz']), torch.from_numpy(D[f'{variant}_pd_dirs']), D[f'{variant}_pd_counts']
+        o = 0
+        for b, n in enumerate(counts):
+            sig, rgb = rp.point_decode(params, xyz[o:o + n], dirs[o:o + n], code[b])
+            _close(sig, D[f'{variant}_pd_sigma'][o:o + n], 1e-5 * float(np.abs(D[f'{variant}_pd_sigma']).max()))
+            _close(rgb, D[f'{variant}_pd_rgb'][o:o + n], 2e-6)
+            o += n
+        # eval branch
+        for b in range(2):
+            r = rp.render_eval_scene(params, ro[b].numpy(), rd[b].numpy(), code[b], bits[b], max_steps=256, dt_gamma=dt_gamma[b])
+            for k in ('weights_sum', 'depth', 'image'):
+                err = float(np.abs(r[k] - D[f'{variant}_eval_{k}'][b]).max())
+                assert err <= 2e-6, (variant, b, k, err)
+            assert float(D[f'{variant}_eval_weights_sum'][b].max()) > 0.5          # the rays do hit something
+    # train branch (variant P): forward, d loss / d code, d loss / d decoder weights
+    g = torch.Generator().manual_seed(int(D['P_code_seed']))
+    code = (torch.randn(2, 3, 6, 128, 128, generator=g) * 0.7).clamp(-2, 2)
+    params = rp.make_decoder_params('P', 4)
+    params['density_net.0.bias'] = params['density_net.0.bias'] + 1.0
+    pref = {k: torch.as_tensor(v).double().requires_grad_(True) for k, v in params.items()}
+    cref = code.double().requires_grad_(True)
+    sel = torch.from_numpy(D['P_train_sel'])
+    gi, gw = torch.from_numpy(D['P_train_gi']).double(), torch.from_numpy(D['P_train_gw']).double()
+    tot = 0
+    for b in range(2):
+        ws, dep, img = tp.render_train_scene(pref, cref[b], ro[b][sel[b]].numpy(), rd[b][sel[b]].numpy(), bits[b], None, dt_gamma=dt_gamma[b])
+        for k, v in (('weights_sum', ws), ('depth', dep), ('image', img)):
+            _close(v.detach(), D[f'P_train_{k}'][b], 5e-6)
+        tot = tot + (img * gi[b]).sum() + (ws * gw[b]).sum()
+    names = [k for k in pref if f'P_train_grad_{k}' in D.files]
+    assert len(names) == 8
+    grads = torch.autograd.grad(tot, [cref] + [pref[k] for k in names])
+    rel = lambda a, b: float((a - torch.from_numpy(b).double()).norm() / np.linalg.norm(b))
+    assert rel(grads[0], D['P_train_grad_code']) < 2e-5, rel(grads[0], D['P_train_grad_code'])
+    for k, gk in zip(names, grads[1:]):
+        assert rel(gk, D[f'P_train_grad_{k}']) < 2e-5, (k, rel(gk, D[f'P_train_grad_{k}']))
+    assert bool(D['P_train_decoder_reg_loss_is_none'])
