@@ -478,3 +478,31 @@ def test_renderer_oracle_matches_reference_decoder_execution():
     for k, gk in zip(names, grads[1:]):
         assert rel(gk, D[f'P_train_grad_{k}']) < 2e-5, (k, rel(gk, D[f'P_train_grad_{k}']))
     assert bool(D['P_train_decoder_reg_loss_is_none'])
+
+
+def test_density_oracle_matches_reference_execution():
+    """`render_port.get_density` / `update_extra_state` (the restatement the GPU occupancy-grid kernels are measured against) vs the fixture
+    produced by executing the reference's own `BaseNeRF.get_density` / `update_extra_state` + `point_density_decode` + morton / packbits
+    wrappers over the kernel-exact C backend (tests/golden/make_golden_density.py): bitfields bit-exact, grid values to fp16 / fp32 round-off."""
+    from oracle import render_port as rp
+    D = np.load(os.path.join(GOLDEN, 'reference_density_v1.npz'))
+    g = torch.Generator().manual_seed(21)
+    code = (torch.randn(2, 3, 6, 128, 128, generator=g) * 0.7).clamp(-2, 2)
+    params = rp.make_decoder_params('P', 6)
+    params['density_net.0.bias'] = params['density_net.0.bias'] - 2.5
+    torch.manual_seed(5)
+    rands = [torch.rand(64 ** 3, 3) for _ in range(3)]                  # the reference draws torch.rand_like(xyzs) once per iteration
+    grid, bits = rp.get_density(params, code, rands, density_thresh=0.1)
+    assert str(grid.dtype) == str(D['gd_grid_dtype']) == 'torch.float16'
+    diff = np.unpackbits(bits) != np.unpackbits(D['gd_bits'])
+    assert diff.mean() <= 2e-5, diff.mean()                              # a voxel exactly at the threshold may flip with 1-ulp decode differences
+    _close(grid.float()[:, ::37], D['gd_grid_sub'], 2e-3 * float(D['gd_grid_sub'].max()))
+    assert abs(float(grid.double().sum()) - float(D['gd_grid_sum'])) <= 1e-4 * float(D['gd_grid_sum'])
+    assert 0.2 < np.unpackbits(D['gd_bits']).mean() < 0.8
+    grid2 = torch.zeros(2, 64 ** 3)
+    torch.manual_seed(6)
+    for i in range(2):
+        bits2, _ = rp.update_extra_state(params, code * (1.0 if i == 0 else 0.5), grid2, torch.rand(64 ** 3, 3), density_thresh=0.08, decay=0.9)
+        _close(grid2[:, ::37], D[f'ue_grid_sub_{i}'], 2e-6 * float(D[f'ue_grid_sub_{i}'].max()) + 1e-7)
+        diff = np.unpackbits(bits2) != np.unpackbits(D[f'ue_bits_{i}'])
+        assert diff.mean() <= 2e-5, (i, diff.mean())
