@@ -1,6 +1,6 @@
 """diagnostic: run-to-run differences of the UNet forward and of the input-gradient pass (same inputs)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import unet_port as up
 from ssdnerf_b200.unet import DenoisingUnetMod

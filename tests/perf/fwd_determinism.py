@@ -1,6 +1,6 @@
 """diagnostic: which forward buffers differ run to run (same input)?  usage: fwd_determinism.py [small|full]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import unet_port as up
 from ssdnerf_b200.unet import DenoisingUnetMod

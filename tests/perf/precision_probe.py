@@ -2,7 +2,7 @@
 (A) GEMM operands (activations + weights), (B) conv outputs that feed a GroupNorm (h1, qkv, attention out), (C) the residual stream
 (block outputs).  Prints rel-L2 vs the un-rounded fp32 forward.  TEST INFRASTRUCTURE (imports oracle/)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.nn.functional as F
 from oracle import unet_port as up

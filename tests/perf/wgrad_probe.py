@@ -5,7 +5,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import train_port as tp  # noqa: E402
 from tests.test_train_render_gpu import _case, _decoder, _rel_l2  # noqa: E402
 from ssdnerf_b200 import renderer as R  # noqa: E402

@@ -178,7 +178,7 @@ def test_small_unet_input_gradient(cuda):
     print('small unet d(v.r)/dx rel l2', err, 'forward', _rel_l2(v, vo))
     assert got.shape == ref.shape and err < 4e-3
     # a second forward + backward agrees to the noise floor of the path: GroupNorm statistics are fp32 atomics, and a 1e-7 perturbation
-    # flips fp16 storage roundings downstream (scripts/fwd_determinism.py: forward run-to-run 1.2e-3, same size as the storage-rounding term)
+    # flips fp16 storage roundings downstream (tests/perf/fwd_determinism.py: forward run-to-run 1.2e-3, same size as the storage-rounding term)
     got2, _, _, _ = _input_grad_case(SMALL, spec, sd, 3, 32, cuda, torch.device('cpu'))
     assert _rel_l2(got2, got) < 4e-3
 

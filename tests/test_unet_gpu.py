@@ -2,7 +2,7 @@
 (oracle/unet_port.py, pinned to the reference's own code by tests/test_reference_pin_cpu.py).
 
 Tolerance.  BASELINE.json north_star: "denoised triplanes within 1e-3 relative fp16 tolerance".  An fp32 oracle cannot be matched to
-1e-3 by ANY single-pass 10/11-bit-mantissa tensor-core path: scripts/precision_probe.py (profiles/r02_precision_probe.txt) injects
+1e-3 by ANY single-pass 10/11-bit-mantissa tensor-core path: tests/perf/precision_probe.py (profiles/r02_precision_probe.txt) injects
 the roundings one at a time into the fp32 oracle at full size -- fp16 GEMM operands alone 1.28e-3, the reference's own default
 (cuDNN TF32 convolutions) 1.28e-3, fp16 storage of h1 +0.62e-3, of the residual stream +0.67e-3 (RSS total
 1.54e-3 = what the GPU measures).  The bars below are therefore stated against that floor: one evaluation <= 2.0e-3 relative L2
