@@ -381,7 +381,7 @@ class BaseNeRF(nn.Module):
         scale = 1 - math.exp(-cfg['loss_coef'] * scale_num_ray) if 'loss_coef' in cfg else 1
         fusable = (isinstance(self.pixel_loss, MSELoss) and (self.reg_loss is None or (isinstance(self.reg_loss, RegLoss) and self.reg_loss.power == 2))
                    and not (return_decoder_loss and decoder.decoder_reg_loss is not None) and isinstance(rays_o, torch.Tensor)
-                   and decoder.training and decoder._fused_train_ok(rays_o, code, self.grid_size))
+                   and decoder.training and hasattr(decoder, '_fused_train_ok') and decoder._fused_train_ok(rays_o, code, self.grid_size))
         if fusable:
             num_scenes = rays_o.size(0)
             rays_o = rays_o.reshape(num_scenes, -1, 3).contiguous().float()

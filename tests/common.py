@@ -98,6 +98,3 @@ class ToyDecoder(torch.nn.Module):
         if return_loss:
             out.update(decoder_reg_loss=None)
         return out
-
-    def _fused_train_ok(self, *args):        # ssdnerf_b200.BaseNeRF.loss asks the decoder whether the fused native route applies
-        return False
